@@ -1,0 +1,185 @@
+/*
+ * vr2.h — C ABI of libvr2.so: the B200 (sm_100a) implementation of the one hot
+ * path Video-R2 spends its rollouts and evaluation in,
+ *
+ *   Qwen2_5_VisionTransformerPretrainedModel.forward(hidden_states, grid_thw)
+ *   Qwen2_5_VLForConditionalGeneration.get_rope_index(input_ids, image_grid_thw,
+ *        video_grid_thw, second_per_grid_ts, attention_mask)
+ *
+ * The reference (mbzuai-oryx/Video-R2) reaches both through Hugging Face
+ * transformers==4.51.1 (requirements.txt:3); its call sites are
+ *   train/src/train/monkey_patch_forward.py:366,374,392   self.visual(pixels, grid_thw=...)
+ *   train/src/train/monkey_patch_forward.py:415-421       self.get_rope_index(...)
+ *   train/src/trainer/grpo_trainer.py:725,783             (stock HF forward / generate)
+ *   eval/lmms-eval/lmms_eval/models/qwen2_5_vl.py:326     (stock HF generate)
+ * and it plugs replacements in by class-attribute assignment
+ * (monkey_patch_forward.py:22-26).  video_r2_b200/patch.py does the same with
+ * functions that call the entry points below through ctypes.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on
+ * success and a negative vr2_status otherwise, with a thread-local message in
+ * vr2_last_error().  Pointers named *_dev are CUDA device pointers of the
+ * current device; everything is enqueued on `stream` (a cudaStream_t passed as
+ * void*) and nothing synchronises unless stated.  There is no CPU fallback:
+ * without a CUDA device every compute entry point fails with VR2_ERR_CUDA.
+ */
+#ifndef VR2_H_
+#define VR2_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum vr2_status {
+  VR2_OK = 0,
+  VR2_ERR_ARG = -1,    /* bad shape / dtype / null pointer (Python shim raises ValueError) */
+  VR2_ERR_CUDA = -2,   /* CUDA runtime or driver error */
+  VR2_ERR_STATE = -3,  /* weights missing, plan/tower mismatch */
+} vr2_status;
+
+typedef enum vr2_dtype {
+  VR2_F32 = 0,
+  VR2_BF16 = 1,
+  VR2_I64 = 2,
+  VR2_I32 = 3,
+  VR2_U8 = 4, /* also torch.bool */
+} vr2_dtype;
+
+const char* vr2_last_error(void);
+int vr2_abi_version(void);
+
+/* ------------------------------------------------------------------------
+ * Index plan: everything the tower derives from grid_thw alone.
+ * Replaces rot_pos_emb (HF modeling_qwen2_5_vl.py:382-409), get_window_index
+ * (:411-451), the unique_consecutive of cu_window_seqlens (:476) and the
+ * cu_seqlens construction (:488-496).  All integer outputs are bit-exact.
+ * ---------------------------------------------------------------------- */
+typedef struct vr2_plan vr2_plan;
+
+typedef struct vr2_plan_config {
+  int32_t spatial_merge_size; /* 2 */
+  int32_t window_size;        /* 112 (pixels) */
+  int32_t patch_size;         /* 14 */
+  int32_t head_dim;           /* 80: rotary table has head_dim/2 angles per patch */
+  float rope_theta;           /* 10000 */
+} vr2_plan_config;
+
+/* grid_thw_host: [n_items,3] int64 on the HOST (t, h, w in patches). Builds the
+ * device tables on `stream`; the plan owns them. */
+int vr2_plan_create(const vr2_plan_config* cfg, const int64_t* grid_thw_host, int32_t n_items, void* stream,
+                    vr2_plan** out);
+void vr2_plan_destroy(vr2_plan* plan);
+int64_t vr2_plan_num_patches(const vr2_plan* plan);     /* N = sum t*h*w */
+int64_t vr2_plan_num_tokens(const vr2_plan* plan);      /* N / merge^2 */
+int64_t vr2_plan_num_windows(const vr2_plan* plan);     /* len(cu_window_seqlens) - 1 after dedupe */
+int64_t vr2_plan_num_slices(const vr2_plan* plan);      /* len(cu_seqlens) - 1 = sum t */
+/* Copies the integer tables into caller buffers (device). Any pointer may be NULL.
+ *   window_index_dev  [tokens]      int64   == HF get_window_index()[0]
+ *   reverse_index_dev [tokens]      int64   == torch.argsort(window_index)
+ *   cu_window_dev     [windows+1]   int32   == unique_consecutive(cu_window_seqlens)
+ *   cu_seqlens_dev    [slices+1]    int32   == F.pad(repeat_interleave(h*w, t).cumsum(0), (1,0))
+ *   pos_hw_dev        [patches,2]   int32   == rot_pos_emb's pos_ids (h, w), original patch order */
+int vr2_plan_export(const vr2_plan* plan, int64_t* window_index_dev, int64_t* reverse_index_dev,
+                    int32_t* cu_window_dev, int32_t* cu_seqlens_dev, int32_t* pos_hw_dev, void* stream);
+/* Rotary angle tables in WINDOW order, fp32 [patches, head_dim/2] each. */
+int vr2_plan_export_rotary(const vr2_plan* plan, float* cos_dev, float* sin_dev, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Bit-exact row gathers (the window permute HF :478-484 and its inverse
+ * :512-513): dst[i, :] = src[index[i], :], rows of row_bytes (multiple of 16).
+ * ---------------------------------------------------------------------- */
+int vr2_gather_rows(const void* src_dev, void* dst_dev, const int64_t* index_dev, int64_t n_rows_out,
+                    int64_t n_rows_in, int64_t row_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
+ * The vision tower.
+ * ---------------------------------------------------------------------- */
+typedef struct vr2_tower vr2_tower;
+
+typedef struct vr2_tower_config {
+  int32_t depth;              /* 32 */
+  int32_t hidden_size;        /* 1280 */
+  int32_t num_heads;          /* 16 */
+  int32_t intermediate_size;  /* 3420 */
+  int32_t out_hidden_size;    /* 3584 */
+  int32_t patch_size;         /* 14 */
+  int32_t temporal_patch_size;/* 2 */
+  int32_t in_channels;        /* 3 */
+  int32_t spatial_merge_size; /* 2 */
+  int32_t window_size;        /* 112 */
+  int32_t n_fullatt;          /* number of valid entries in fullatt_block_indexes */
+  int32_t fullatt_block_indexes[8]; /* 7,15,23,31 */
+  float rms_norm_eps;         /* 1e-6 */
+  float rope_theta;           /* 10000 */
+} vr2_tower_config;
+
+int vr2_tower_create(const vr2_tower_config* cfg, int32_t cuda_device, vr2_tower** out);
+void vr2_tower_destroy(vr2_tower* tower);
+/* One call per entry of the HF module's state_dict (names relative to the
+ * vision module: "patch_embed.proj.weight", "blocks.0.norm1.weight",
+ * "blocks.0.attn.qkv.weight", ..., "merger.mlp.2.bias").  The tensor is read on
+ * `stream`, converted and repacked into library-owned bf16/fp32 storage; the
+ * caller's buffer is not retained.  dtype: VR2_F32 or VR2_BF16. */
+int vr2_tower_set_weight(vr2_tower* tower, const char* name, const void* data_dev, int32_t dtype,
+                         const int64_t* shape, int32_t ndim, void* stream);
+/* Fails with VR2_ERR_STATE and lists what is missing unless every tensor was set. */
+int vr2_tower_finalize(vr2_tower* tower);
+size_t vr2_tower_workspace_bytes(const vr2_tower* tower, int64_t n_patches);
+/* pixels_dev: [N, 1176] (dtype VR2_F32 or VR2_BF16), rows ordered as the HF
+ * processor emits them; out_dev: [N/4, out_hidden] (VR2_BF16 or VR2_F32) in the
+ * ORIGINAL token order (inverse window permute applied), i.e. exactly what
+ * transformers 4.51.1 returns from visual.forward. workspace_dev: at least
+ * vr2_tower_workspace_bytes() bytes, 1024-byte aligned. */
+int vr2_tower_forward(vr2_tower* tower, const vr2_plan* plan, const void* pixels_dev, int32_t pixels_dtype,
+                      void* out_dev, int32_t out_dtype, void* workspace_dev, size_t workspace_bytes, void* stream);
+/* Number of kernels vr2_tower_forward enqueues for this plan (for gpu_launches). */
+int64_t vr2_tower_launch_count(const vr2_tower* tower, const vr2_plan* plan, int32_t pixels_dtype);
+
+/* ------------------------------------------------------------------------
+ * get_rope_index, transformers 4.51.1 semantics.
+ * ---------------------------------------------------------------------- */
+typedef struct vr2_rope_config {
+  int32_t spatial_merge_size;   /* 2 */
+  int64_t image_token_id;       /* 151655 */
+  int64_t video_token_id;       /* 151656 */
+  int64_t vision_start_token_id;/* 151652 */
+  float tokens_per_second;      /* 2 */
+  /* how second_per_grid_t enters the temporal index:
+   *   0: t = trunc(fp32(fp32(k * spg) * tps))      (float multiply, then .long())
+   *   1: t = k * trunc(spg) * tps                  (as_tensor(..., dtype=int64) first) */
+  int32_t spg_int_cast;
+} vr2_rope_config;
+
+/* input_ids_dev [B,S] int64; mask_dev [B,S] of mask_dtype (I64/I32/U8) or NULL;
+ * image_thw_dev [n_img,3] / video_thw_dev [n_vid,3] int64 or NULL;
+ * second_per_grid_ts_dev [n_vid] fp32 or NULL;
+ * scratch_dev: B*S int32 + 2*B int32 (vr2_rope_scratch_bytes);
+ * position_ids_dev [3,B,S] int64; deltas_dev [B] int64.
+ * With both grids NULL this is the text-only branch. */
+size_t vr2_rope_scratch_bytes(int32_t B, int32_t S);
+int vr2_rope_index(const vr2_rope_config* cfg, const int64_t* input_ids_dev, const void* mask_dev, int32_t mask_dtype,
+                   int32_t B, int32_t S, const int64_t* image_thw_dev, int32_t n_img, const int64_t* video_thw_dev,
+                   int32_t n_vid, const float* second_per_grid_ts_dev, void* scratch_dev, int64_t* position_ids_dev,
+                   int64_t* deltas_dev, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Single operators, exported so tests can pin each kernel against the oracle.
+ * ---------------------------------------------------------------------- */
+/* C[M,N] = A[M,K] W[N,K]^T (+bias) (GELU optional); A, W bf16; out bf16 or fp32. */
+int vr2_op_linear(const void* a_dev, const void* w_dev, const float* bias_dev, void* out_dev, int32_t out_dtype,
+                  int32_t M, int32_t N, int32_t K, int32_t gelu, void* stream);
+/* out = bf16(x * rsqrt(mean(x^2)+eps) * w), x fp32 [rows, dim]. */
+int vr2_op_rmsnorm(const float* x_dev, const float* w_dev, void* out_bf16_dev, int64_t rows, int32_t dim, float eps,
+                   void* stream);
+/* Varlen attention: qkv bf16 [N, 3*heads*80] (rotary already applied), cu_seqlens_host int32 [n_seq+1] (HOST),
+ * out bf16 [N, heads*80]. Synchronises the stream (test helper). */
+int vr2_op_attention(const void* qkv_dev, void* out_dev, const int32_t* cu_seqlens_host, int32_t n_seq,
+                     int32_t num_heads, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VR2_H_ */

@@ -1,0 +1,99 @@
+"""Generates the golden fixtures in this directory by running the REFERENCE arithmetic —
+the Hugging Face `Qwen2_5_VisionTransformerPretrainedModel` that Video-R2 calls
+(train/src/train/monkey_patch_forward.py:392) — in the build container:
+
+    python tests/golden/make_golden.py
+
+transformers 5.5.0 is what is installed here (Video-R2 pins 4.51.1; SURVEY §8c shows
+the vision-tower math is unchanged between them, only the return type is).  The
+fixtures pin oracle/indices.py and oracle/tower.py; the GPU tests then compare the
+CUDA path with the oracle and with these files.
+
+  indices_<name>.npz  window_index, raw + deduped cu_window_seqlens, rot_pos_emb output of
+                      HF get_window_index / rot_pos_emb
+  tower_<name>.npz    fp32 `.pooler_output` of the HF module (attn_implementation="sdpa") on
+                      seeded weights (oracle.tower.make_weights) and seeded pixels; inputs are
+                      regenerated from the seeds, their checksums are stored
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+
+from oracle import tower as otower  # noqa: E402
+
+INDEX_GRIDS = {
+    "docstring_4x12x20": [[4, 12, 20]],
+    "cfg1_8x32x32": [[8, 32, 32]],
+    "zero3_dummy_1x28x28": [[1, 28, 28]],
+    "tiny_1x2x2": [[1, 2, 2]],
+    "odd_merged_3x26x46": [[3, 26, 46]],
+    "multi_clip": [[2, 10, 14], [1, 4, 6], [3, 26, 46], [1, 8, 8]],
+    "cfg4_slice_2x24x42": [[2, 24, 42]],
+}
+
+TOWER_CASES = {
+    # name: (depth, fullatt, grid, weight seed, pixel seed)
+    "depth32_ragged": (32, (7, 15, 23, 31), [[2, 8, 12], [1, 4, 6]], 11, 12),
+    "depth4_odd": (4, (1, 3), [[1, 10, 14], [2, 6, 4]], 21, 22),
+}
+
+
+def hf_model(depth, full):
+    from transformers.models.qwen2_5_vl.configuration_qwen2_5_vl import Qwen2_5_VLVisionConfig
+    from transformers.models.qwen2_5_vl.modeling_qwen2_5_vl import Qwen2_5_VisionTransformerPretrainedModel as V
+
+    cfg = Qwen2_5_VLVisionConfig(depth=depth, hidden_size=1280, intermediate_size=3420, num_heads=16,
+                                 out_hidden_size=3584, patch_size=14, spatial_merge_size=2, temporal_patch_size=2,
+                                 window_size=112, fullatt_block_indexes=list(full), tokens_per_second=2,
+                                 hidden_act="silu")
+    cfg._attn_implementation = "sdpa"
+    return V._from_config(cfg).eval().float()
+
+
+def seeded_pixels(n, seed):
+    x = torch.randn(n, 1176, generator=torch.Generator().manual_seed(seed))
+    return x.to(torch.bfloat16).to(torch.float32)  # bf16-exact, like normalised frames cast by the caller
+
+
+def checksum(t: torch.Tensor) -> np.ndarray:
+    t = t.double().reshape(-1)
+    return np.array([t.sum().item(), t.abs().sum().item(), t[:: max(1, t.numel() // 97)].sum().item()])
+
+
+def main():
+    m = hf_model(1, [0])
+    for name, grid in INDEX_GRIDS.items():
+        g = torch.tensor(grid)
+        wi, cu = m.get_window_index(g)
+        dedup = torch.unique_consecutive(torch.tensor(cu, dtype=torch.int32))
+        rot = m.rot_pos_emb(g)
+        np.savez_compressed(os.path.join(HERE, f"indices_{name}.npz"), grid=np.asarray(grid, dtype=np.int64),
+                            window_index=wi.numpy().astype(np.int64), cu_raw=np.asarray(cu, dtype=np.int64),
+                            cu_dedup=dedup.numpy().astype(np.int32), rot_pos_emb=rot.numpy().astype(np.float32))
+        print("indices", name, wi.shape, len(cu), dedup.shape)
+    for name, (depth, full, grid, wseed, pseed) in TOWER_CASES.items():
+        cfg = otower.TowerConfig(depth=depth, fullatt_block_indexes=tuple(full))
+        w = otower.make_weights(cfg, seed=wseed)
+        m = hf_model(depth, full)
+        m.load_state_dict(w, strict=True)
+        n = sum(t * h * ww for t, h, ww in grid)
+        x = seeded_pixels(n, pseed)
+        with torch.no_grad():
+            res = m(x, grid_thw=torch.tensor(grid))
+        out = res.pooler_output if hasattr(res, "pooler_output") else res
+        wsum = np.stack([checksum(w[k]) for k in sorted(w)][:8])
+        np.savez_compressed(os.path.join(HERE, f"tower_{name}.npz"), grid=np.asarray(grid, dtype=np.int64),
+                            depth=depth, fullatt=np.asarray(full), weight_seed=wseed, pixel_seed=pseed,
+                            out=out.numpy().astype(np.float32), pixel_checksum=checksum(x), weight_checksum=wsum)
+        print("tower", name, out.shape, float(out.abs().max()))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,64 @@
+"""GPU: each CUDA kernel against a plain fp32 PyTorch reference of the same op, through the C ABI."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf16(shape, seed, scale=1.0, dev="cuda"):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(torch.bfloat16).to(dev)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 128), (200, 264, 1176), (1000, 1280, 1280),
+                                   (8192, 1280, 3456), (513, 3584, 5120), (16384, 5120, 1280)])
+def test_linear_matches_fp32(M, N, K):
+    from video_r2_b200 import ops
+    a, w = _bf16((M, K), 1), _bf16((N, K), 2, 0.05)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(3)).cuda()
+    out = ops.linear(a, w, bias)
+    ref = a.float() @ w.float().T + bias
+    err = (out - ref).abs().max().item()
+    # fp32 accumulation of exact bf16 products: only summation order differs
+    assert err < 2e-3 * math.sqrt(K / 64), (M, N, K, err)
+    out_b = ops.linear(a, w, bias, gelu=True, out_dtype=torch.bfloat16)
+    ref_b = torch.nn.functional.gelu(ref)
+    assert (out_b.float() - ref_b).abs().max().item() < 0.03 * max(1.0, ref_b.abs().max().item() / 4)
+
+
+def test_rmsnorm_matches_fp32():
+    from video_r2_b200 import ops
+    x = torch.randn(777, 1280, generator=torch.Generator().manual_seed(1)).cuda() * 3
+    w = (1 + 0.1 * torch.randn(1280, generator=torch.Generator().manual_seed(2))).cuda()
+    out = ops.rmsnorm(x, w, 1e-6)
+    ref = w * (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6))
+    assert (out.float() - ref).abs().max().item() <= ref.abs().max().item() * 2 ** -8
+
+
+def _attn_ref(qkv, cu, heads):
+    N = qkv.shape[0]
+    q, k, v = qkv.float().reshape(N, 3, heads, 80).unbind(1)
+    out = torch.empty(N, heads, 80, device=qkv.device)
+    for i in range(len(cu) - 1):
+        s, e = cu[i], cu[i + 1]
+        if e == s:
+            continue
+        att = torch.einsum("qhd,khd->hqk", q[s:e], k[s:e]) / math.sqrt(80)
+        out[s:e] = torch.einsum("hqk,khd->qhd", att.softmax(-1), v[s:e])
+    return out.reshape(N, heads * 80)
+
+
+@pytest.mark.parametrize("lens", [[64] * 6, [4, 16, 64, 32, 8, 48, 12], [1024], [1008, 720], [100, 1, 63, 65, 129]])
+def test_attention_varlen_matches_fp32(lens):
+    from video_r2_b200 import ops
+    heads = 16
+    cu = [0]
+    for L in lens:
+        cu.append(cu[-1] + L)
+    qkv = _bf16((cu[-1], 3 * heads * 80), 7)
+    out = ops.attention(qkv, cu, heads)
+    ref = _attn_ref(qkv, cu, heads)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 2e-2, err  # P and the output are rounded to bf16

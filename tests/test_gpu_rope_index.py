@@ -1,0 +1,67 @@
+"""GPU: vr2.get_rope_index is bit-exact against the oracle restatement of transformers 4.51.1."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rope_index as R
+from rope_cases import VID, VS, build_row, case_suite, pad_batch
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu(kw):
+    out = {}
+    for k, v in kw.items():
+        out[k] = v.cuda() if isinstance(v, torch.Tensor) else v
+    return out
+
+
+def _run_both(kw, int_cast):
+    import video_r2_b200 as vr2
+    cfg = vr2.RopeConfig(spg_int_cast=int_cast)
+    g = _gpu(kw)
+    pos, delta = vr2.get_rope_index(g["input_ids"], g.get("image_grid_thw"), g.get("video_grid_thw"),
+                                    g.get("second_per_grid_ts"), g.get("attention_mask"), config=cfg)
+    rpos, rdelta = R.get_rope_index(kw["input_ids"], kw.get("image_grid_thw"), kw.get("video_grid_thw"),
+                                    kw.get("second_per_grid_ts"), kw.get("attention_mask"), spg_int_cast=int_cast)
+    return pos.cpu(), delta.cpu(), rpos, rdelta
+
+
+@pytest.mark.parametrize("int_cast", [True, False], ids=["int64cast", "float32mul"])
+@pytest.mark.parametrize("name,kw", case_suite(), ids=[c[0] for c in case_suite()])
+def test_bit_exact_vs_oracle(name, kw, int_cast):
+    pos, delta, rpos, rdelta = _run_both(kw, int_cast)
+    assert pos.dtype == torch.int64 and pos.shape == rpos.shape and delta.shape == rdelta.shape
+    assert torch.equal(pos, rpos), name
+    assert torch.equal(delta, rdelta.to(torch.int64)), name
+
+
+def test_fp32_truncation_known_answers():
+    import video_r2_b200 as vr2
+    ids = torch.tensor([[VS] + [VID] * 12 + [151653]]).cuda()
+    grid = torch.tensor([[12, 2, 2]]).cuda()
+    for spg, ef, ei in [(0.7, [0, 1, 2, 4, 5, 7, 8, 9, 11, 12, 14, 15], [0] * 12),
+                        (9.375, [0, 18, 37, 56, 75, 93, 112, 131, 150, 168, 187, 206], [18 * k for k in range(12)])]:
+        pos, _ = vr2.get_rope_index(ids, None, grid, torch.tensor([spg]).cuda(), None, config=vr2.RopeConfig(spg_int_cast=False))
+        assert (pos[0, 0, 1:13] - 1).tolist() == ef
+        pos, _ = vr2.get_rope_index(ids, None, grid, [spg], None, config=vr2.RopeConfig(spg_int_cast=True))
+        assert (pos[0, 0, 1:13] - 1).tolist() == ei
+
+
+@pytest.mark.parametrize("int_cast", [True, False])
+def test_config2_sequence_and_long_batch(int_cast):
+    """BASELINE config 2: a 32-frame 448x448 clip = 4096 video tokens + text; plus a ragged 6-row batch."""
+    rng = np.random.default_rng(5)
+    g = [16, 32, 32]
+    row = build_row([(VID, g)], rng, lead=32, gap=0, tail=64)
+    kw = dict(input_ids=torch.tensor([row]), video_grid_thw=torch.tensor([g]), second_per_grid_ts=torch.tensor([2 / 0.7]))
+    pos, delta, rpos, rdelta = _run_both(kw, int_cast)
+    assert torch.equal(pos, rpos) and torch.equal(delta, rdelta)
+    grids = [[int(rng.integers(1, 9)), int(rng.integers(2, 12)) * 2, int(rng.integers(2, 12)) * 2] for _ in range(6)]
+    rows = [build_row([(VID, gg)], rng, lead=int(rng.integers(0, 40)), gap=int(rng.integers(0, 5)), tail=int(rng.integers(0, 50))) for gg in grids]
+    for side in ("left", "right"):
+        ids, mask = pad_batch(rows, side)
+        kw = dict(input_ids=ids, attention_mask=mask, video_grid_thw=torch.tensor(grids),
+                  second_per_grid_ts=torch.tensor([2 / f for f in (2.0, 1.0, 0.2133, 0.7, 3.0, 1.7)]))
+        pos, delta, rpos, rdelta = _run_both(kw, int_cast)
+        assert torch.equal(pos, rpos) and torch.equal(delta, rdelta)

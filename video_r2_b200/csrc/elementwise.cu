@@ -1,0 +1,101 @@
+// HBM-bound helpers: dtype casts, weight repacking at load time, and the one
+// stand-alone RMSNorm the tower still needs (ln_q of the PatchMerger, HF
+// modeling_qwen2_5_vl.py:57-71,:144-146 — the per-block norms are folded into the
+// GEMM epilogues).  Vectorised 16-byte accesses, warp-shuffle reductions, grids
+// sized in multiples of the SM count.
+#include "elementwise.cuh"
+
+#include <cuda_bf16.h>
+
+#include "ptx.cuh"
+
+namespace vr2 {
+
+namespace {
+
+__global__ void cast_f32_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, int64_t n_vec) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 v = __ldg(src + i);
+    dst[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  }
+}
+
+// one warp per row; dim % 128 == 0 (32 lanes x float4)
+__global__ void rmsnorm_bf16_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                    __nv_bfloat16* __restrict__ out, int64_t rows, int dim, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
+  for (int64_t row = warp0; row < rows; row += nwarps) {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * dim);
+    float ss = 0.f;
+    for (int v = lane; v < dim / 4; v += 32) {
+      const float4 a = xr[v];
+      ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss / static_cast<float>(dim) + eps);
+    uint2* orow = reinterpret_cast<uint2*>(out + row * dim);
+    for (int v = lane; v < dim / 4; v += 32) {
+      const float4 a = xr[v];
+      const float4 g = __ldg(reinterpret_cast<const float4*>(w) + v);
+      orow[v] = make_uint2(pack_bf16x2(a.x * rstd * g.x, a.y * rstd * g.y), pack_bf16x2(a.z * rstd * g.z, a.w * rstd * g.w));
+    }
+  }
+}
+
+template <typename Src, typename Dst>
+__global__ void repack_kernel(const Src* __restrict__ src, int64_t rows, int64_t cols, Dst* __restrict__ dst,
+                              int64_t ld_dst, int64_t blk, int64_t blk_stride, int64_t offset) {
+  const int64_t total = rows * cols;
+  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = e / cols, c = e - r * cols;
+    const int64_t dr = (r / blk) * blk_stride + offset + (r % blk);
+    float v;
+    if constexpr (sizeof(Src) == 2) v = __bfloat162float(src[e]); else v = static_cast<float>(src[e]);
+    if constexpr (sizeof(Dst) == 2) dst[dr * ld_dst + c] = __float2bfloat16_rn(v); else dst[dr * ld_dst + c] = v;
+  }
+}
+
+int grid_for(int64_t work_items, int threads) {
+  int64_t blocks = (work_items + threads - 1) / threads;
+  const int64_t cap = 148 * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+}  // namespace
+
+cudaError_t cast_f32_to_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t stream) {
+  if (n % 4 != 0) return cudaErrorInvalidValue;
+  cast_f32_bf16_kernel<<<grid_for(n / 4, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(src),
+                                                                  reinterpret_cast<uint2*>(dst), n / 4);
+  return cudaGetLastError();
+}
+
+cudaError_t rmsnorm_to_bf16(const float* x, const float* w, __nv_bfloat16* out, int64_t rows, int dim, float eps,
+                            cudaStream_t stream) {
+  if (dim % 4 != 0) return cudaErrorInvalidValue;
+  rmsnorm_bf16_kernel<<<grid_for(rows * 32, 256), 256, 0, stream>>>(x, w, out, rows, dim, eps);
+  return cudaGetLastError();
+}
+
+cudaError_t repack_matrix(const void* src, bool src_bf16, int64_t rows, int64_t cols, void* dst, bool dst_bf16,
+                          int64_t ld_dst, int64_t blk, int64_t blk_stride, int64_t offset, cudaStream_t stream) {
+  const int g = grid_for(rows * cols, 256);
+  if (src_bf16 && dst_bf16)
+    repack_kernel<<<g, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(src), rows, cols, static_cast<__nv_bfloat16*>(dst), ld_dst, blk, blk_stride, offset);
+  else if (src_bf16)
+    repack_kernel<<<g, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(src), rows, cols, static_cast<float*>(dst), ld_dst, blk, blk_stride, offset);
+  else if (dst_bf16)
+    repack_kernel<<<g, 256, 0, stream>>>(static_cast<const float*>(src), rows, cols, static_cast<__nv_bfloat16*>(dst), ld_dst, blk, blk_stride, offset);
+  else
+    repack_kernel<<<g, 256, 0, stream>>>(static_cast<const float*>(src), rows, cols, static_cast<float*>(dst), ld_dst, blk, blk_stride, offset);
+  return cudaGetLastError();
+}
+
+}  // namespace vr2

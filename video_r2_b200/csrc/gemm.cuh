@@ -1,0 +1,60 @@
+// Internal (C++) interface of the tcgen05 GEMM used by every dense layer of the
+// tower.  C[M,N] = A[M,K] * W[N,K]^T with A and W bf16, K-major; fp32 accumulate
+// in TMEM; the epilogue variant decides what is written.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace vr2 {
+
+enum GemmEpilogue : int {
+  EPI_STORE = 0,   // out = act(acc + bias) -> fp32 or bf16, optional destination-row map
+  EPI_RESID = 1,   // x = [x +] acc + bias (fp32, in place); xb = bf16(x * norm_w); ssq partials
+  EPI_QKV = 2,     // v = acc*rstd + bias; 2-D rotary on q,k heads; bf16 [M,3840]
+  EPI_SWIGLU = 3,  // h = silu(g*rstd+bg) * (u*rstd+bu), gate/up interleaved per 256-column tile
+};
+
+enum GemmFlags : int {
+  GEMM_ADD_RESID = 1,  // EPI_RESID: read-modify-write x
+  GEMM_GELU = 2,       // EPI_STORE: exact-erf GELU
+  GEMM_OUT_F32 = 4,    // EPI_STORE: fp32 output (else bf16)
+};
+
+struct GemmArgs {
+  // operands (device pointers, bf16, row-major, leading dimension in elements)
+  const __nv_bfloat16* A;
+  int64_t lda;
+  const __nv_bfloat16* W;
+  int64_t ldw;
+  int M, N, K;
+  int epilogue;
+  int flags;
+  // epilogue operands
+  const float* bias;       // [N] fp32 or null
+  float* x;                // EPI_RESID: residual stream fp32 [rows, ldx]
+  int64_t ldx;
+  __nv_bfloat16* out_bf16; // bf16 output (EPI_STORE / xb of EPI_RESID / qkv / h)
+  float* out_f32;          // EPI_STORE fp32 output
+  int64_t ld_out;
+  const int* row_map;      // destination row of source row r (null = identity)
+  const float* norm_w;     // EPI_RESID: weight of the RMSNorm that reads x next, [N]
+  float* ssq;              // partial sum of squares: written [rows, N/256] by EPI_RESID
+  const float* ssq_in;     // read by EPI_QKV / EPI_SWIGLU, [M, ssq_parts]
+  int ssq_parts;
+  float inv_dim;           // 1 / hidden
+  float eps;
+  const float* cos_tab;    // EPI_QKV: [M, 40] fp32
+  const float* sin_tab;
+};
+
+// Enqueues the GEMM on `stream`.  Returns cudaSuccess or the launch error; shape
+// violations set *err_msg (static string) and return cudaErrorInvalidValue.
+cudaError_t gemm_launch(const GemmArgs& args, int num_sms, cudaStream_t stream, const char** err_msg);
+
+// Resolves cuTensorMapEncodeTiled through the runtime (no link against libcuda).
+bool tma_encode_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
+                        uint32_t box_inner, uint32_t box_rows);
+
+}  // namespace vr2

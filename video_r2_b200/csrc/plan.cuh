@@ -1,0 +1,33 @@
+// Index plan: every table the tower derives from grid_thw alone (internal view).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <vector>
+
+struct vr2_plan {
+  int device = 0;
+  int merge = 2;         // spatial_merge_size
+  int win_tokens = 4;    // window edge in merged tokens (window_size / merge / patch)
+  int half_dim = 40;     // rotary angles per patch (head_dim / 2)
+  int64_t n_patches = 0;
+  int64_t n_tokens = 0;
+  int64_t n_windows = 0; // non-empty windows
+  int64_t n_slices = 0;
+  int64_t n_tiles_window = 0;
+  int64_t n_tiles_full = 0;
+  std::vector<int64_t> grid;  // host copy [n_items*3]
+
+  // device tables (one allocation, carved)
+  void* blob = nullptr;
+  int64_t* window_index = nullptr;   // [tokens]
+  int64_t* reverse_index = nullptr;  // [tokens]
+  int32_t* row_map = nullptr;        // [patches] original patch row -> window-order row
+  int32_t* out_map = nullptr;        // [tokens]  window-order token -> original token (== window_index)
+  int32_t* pos_hw = nullptr;         // [patches,2] original order
+  float* cos_tab = nullptr;          // [patches, half_dim] window order
+  float* sin_tab = nullptr;
+  int32_t* cu_window = nullptr;      // [windows+1]
+  int32_t* cu_seqlens = nullptr;     // [slices+1]
+  int4* tiles_window = nullptr;      // attention query tiles for window layers
+  int4* tiles_full = nullptr;        // ... for full-attention layers
+};

@@ -1,0 +1,476 @@
+// The vision tower behind the C ABI: weight ingestion (HF state_dict names ->
+// library-owned, repacked bf16 / fp32 storage) and the forward schedule
+// (HF modeling_qwen2_5_vl.py:455-518) expressed as 5 launches per block:
+//
+//   qkv   GEMM  A = bf16(x * w_norm1)   epilogue: * rstd(x), + bias, 2-D rotary      -> qkv  bf16 [N,3840]
+//   attn        varlen flash attention over window / slice segments                  -> att  bf16 [N,1280]
+//   proj  GEMM  epilogue: x += acc + bias; xb = bf16(x * w_norm2); partial sum x^2   -> x fp32, xb, ssq
+//   gate|up GEMM (interleaved 128-column groups) epilogue: * rstd, + bias, SiLU*up   -> h    bf16 [N,3456]
+//   down  GEMM  epilogue: x += acc + bias; xb = bf16(x * w_norm1[next]); ssq
+//
+// RMSNorm never runs as a kernel inside the blocks: x * rsqrt(mean x^2 + eps) * w
+// feeds a linear layer, so the row scale rstd commutes with the GEMM and is
+// applied to the fp32 accumulator, while w is multiplied in (fp32) before the
+// single bf16 rounding of the operand.  The residual stream x stays fp32 in HBM.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "attention.cuh"
+#include "common.cuh"
+#include "elementwise.cuh"
+#include "gemm.cuh"
+#include "plan.cuh"
+
+namespace vr2 {
+
+std::string& last_error_ref() {
+  thread_local std::string s;
+  return s;
+}
+
+namespace {
+
+struct Tensor {
+  void* ptr = nullptr;
+  bool set = false;
+};
+
+struct Layer {
+  Tensor norm1_w, norm2_w;        // fp32 [hidden]
+  Tensor qkv_w, qkv_b;            // bf16 [3h, h], fp32 [3h]
+  Tensor proj_w, proj_b;          // bf16 [h, h], fp32 [h]
+  Tensor gu_w, gu_b;              // bf16 [2*ipad, h] interleaved per 128, fp32 [2*ipad]
+  bool gate_w_set = false, up_w_set = false, gate_b_set = false, up_b_set = false;
+  Tensor down_w, down_b;          // bf16 [h, ipad], fp32 [h]
+};
+
+}  // namespace
+}  // namespace vr2
+
+struct vr2_tower {
+  vr2_tower_config cfg;
+  int device = 0;
+  int num_sms = 148;
+  int head_dim = 80;
+  int ipad = 3456;        // intermediate padded to a multiple of 128
+  int patch_k = 1176;     // in_channels * temporal_patch * patch * patch
+  int merge_dim = 5120;   // hidden * merge^2
+  bool finalized = false;
+  std::vector<vr2::Layer> layers;
+  vr2::Tensor patch_w;             // bf16 [h, patch_k]
+  vr2::Tensor lnq_w;               // fp32 [h]
+  vr2::Tensor fc1_w, fc1_b;        // bf16 [md, md], fp32 [md]
+  vr2::Tensor fc2_w, fc2_b;        // bf16 [out, md], fp32 [out]
+  std::vector<void*> allocs;
+};
+
+using namespace vr2;
+
+namespace {
+
+int alloc_zero(vr2_tower* t, Tensor* dst, size_t bytes) {
+  void* p = nullptr;
+  VR2_CUDA(cudaMalloc(&p, bytes));
+  VR2_CUDA(cudaMemset(p, 0, bytes));
+  t->allocs.push_back(p);
+  dst->ptr = p;
+  return VR2_OK;
+}
+
+bool is_full_layer(const vr2_tower* t, int l) {
+  for (int i = 0; i < t->cfg.n_fullatt; ++i)
+    if (t->cfg.fullatt_block_indexes[i] == l) return true;
+  return false;
+}
+
+}  // namespace
+
+extern "C" const char* vr2_last_error(void) { return last_error_ref().c_str(); }
+extern "C" int vr2_abi_version(void) { return 1; }
+
+extern "C" int vr2_tower_create(const vr2_tower_config* cfg, int32_t device, vr2_tower** out) {
+  if (cfg == nullptr || out == nullptr) return fail(VR2_ERR_ARG, "vr2_tower_create: null argument");
+  if (cfg->depth <= 0 || cfg->num_heads <= 0 || cfg->hidden_size % cfg->num_heads != 0)
+    return fail(VR2_ERR_ARG, "vr2_tower_create: bad depth/heads/hidden");
+  const int head_dim = cfg->hidden_size / cfg->num_heads;
+  if (head_dim != 80) return fail(VR2_ERR_ARG, "vr2_tower_create: head_dim %d unsupported (kernels are built for 80)", head_dim);
+  if (cfg->hidden_size % 256 != 0 || (3 * cfg->hidden_size) % 240 != 0)
+    return fail(VR2_ERR_ARG, "vr2_tower_create: hidden_size %d must be a multiple of 1280", cfg->hidden_size);
+  if (cfg->spatial_merge_size != 2) return fail(VR2_ERR_ARG, "vr2_tower_create: spatial_merge_size must be 2");
+  if (cfg->out_hidden_size % 8 != 0) return fail(VR2_ERR_ARG, "vr2_tower_create: out_hidden_size must be a multiple of 8");
+  if (cfg->n_fullatt < 0 || cfg->n_fullatt > 8) return fail(VR2_ERR_ARG, "vr2_tower_create: n_fullatt out of range");
+  const int patch_k = cfg->in_channels * cfg->temporal_patch_size * cfg->patch_size * cfg->patch_size;
+  if (patch_k % 8 != 0) return fail(VR2_ERR_ARG, "vr2_tower_create: patch row of %d elements is not 16-byte aligned", patch_k);
+  int n_dev = 0;
+  cudaError_t e = cudaGetDeviceCount(&n_dev);
+  if (e != cudaSuccess || n_dev <= device)
+    return fail(VR2_ERR_CUDA, "vr2_tower_create: CUDA device %d not available (%s); there is no CPU path", device,
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count too small");
+  VR2_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  VR2_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(VR2_ERR_CUDA, "vr2_tower_create: device is sm_%d%d; this library contains sm_100a code only", prop.major, prop.minor);
+
+  auto* t = new vr2_tower();
+  t->cfg = *cfg;
+  t->device = device;
+  t->num_sms = prop.multiProcessorCount;
+  t->head_dim = head_dim;
+  t->ipad = (cfg->intermediate_size + 127) / 128 * 128;
+  t->patch_k = patch_k;
+  t->merge_dim = cfg->hidden_size * cfg->spatial_merge_size * cfg->spatial_merge_size;
+  t->layers.resize(cfg->depth);
+  const size_t h = cfg->hidden_size, ip = t->ipad, md = t->merge_dim, oh = cfg->out_hidden_size;
+  int rc = VR2_OK;
+  auto A = [&](Tensor* x, size_t bytes) { if (rc == VR2_OK) rc = alloc_zero(t, x, bytes); };
+  A(&t->patch_w, h * patch_k * 2);
+  A(&t->lnq_w, h * 4);
+  A(&t->fc1_w, md * md * 2);
+  A(&t->fc1_b, md * 4);
+  A(&t->fc2_w, oh * md * 2);
+  A(&t->fc2_b, oh * 4);
+  for (auto& L : t->layers) {
+    A(&L.norm1_w, h * 4);
+    A(&L.norm2_w, h * 4);
+    A(&L.qkv_w, 3 * h * h * 2);
+    A(&L.qkv_b, 3 * h * 4);
+    A(&L.proj_w, h * h * 2);
+    A(&L.proj_b, h * 4);
+    A(&L.gu_w, 2 * ip * h * 2);
+    A(&L.gu_b, 2 * ip * 4);
+    A(&L.down_w, h * ip * 2);
+    A(&L.down_b, h * 4);
+  }
+  if (rc != VR2_OK) {
+    vr2_tower_destroy(t);
+    return rc;
+  }
+  *out = t;
+  return VR2_OK;
+}
+
+extern "C" void vr2_tower_destroy(vr2_tower* t) {
+  if (t == nullptr) return;
+  for (void* p : t->allocs) cudaFree(p);
+  delete t;
+}
+
+extern "C" int vr2_tower_set_weight(vr2_tower* t, const char* name, const void* data, int32_t dtype,
+                                    const int64_t* shape, int32_t ndim, void* stream_v) {
+  if (t == nullptr || name == nullptr || data == nullptr || shape == nullptr)
+    return fail(VR2_ERR_ARG, "vr2_tower_set_weight: null argument");
+  if (dtype != VR2_F32 && dtype != VR2_BF16)
+    return fail(VR2_ERR_ARG, "vr2_tower_set_weight(%s): dtype %d unsupported (fp32/bf16)", name, dtype);
+  cudaStream_t s = as_stream(stream_v);
+  const bool sb = dtype == VR2_BF16;
+  int64_t numel = 1;
+  for (int i = 0; i < ndim; ++i) numel *= shape[i];
+  const int64_t h = t->cfg.hidden_size, inter = t->cfg.intermediate_size, ip = t->ipad, md = t->merge_dim,
+                oh = t->cfg.out_hidden_size;
+  const int64_t huge = int64_t(1) << 40;
+
+  // dst rows = src rows unless (blk, stride, off) say otherwise
+  auto mat = [&](Tensor* dst, bool dst_bf16, int64_t rows, int64_t cols, int64_t ld, int64_t blk, int64_t stride,
+                 int64_t off) -> int {
+    if (numel != rows * cols)
+      return fail(VR2_ERR_ARG, "vr2_tower_set_weight(%s): expected %lld x %lld = %lld elements, got %lld", name,
+                  (long long)rows, (long long)cols, (long long)(rows * cols), (long long)numel);
+    VR2_CUDA(repack_matrix(data, sb, rows, cols, dst->ptr, dst_bf16, ld, blk, stride, off, s));
+    dst->set = true;
+    return VR2_OK;
+  };
+  auto W = [&](Tensor* dst, int64_t rows, int64_t cols, int64_t ld) { return mat(dst, true, rows, cols, ld, huge, 0, 0); };
+  auto V = [&](Tensor* dst, int64_t n) { return mat(dst, false, 1, n, n, huge, 0, 0); };
+
+  const std::string n(name);
+  if (n == "patch_embed.proj.weight") return W(&t->patch_w, h, t->patch_k, t->patch_k);
+  if (n == "merger.ln_q.weight") return V(&t->lnq_w, h);
+  if (n == "merger.mlp.0.weight") return W(&t->fc1_w, md, md, md);
+  if (n == "merger.mlp.0.bias") return V(&t->fc1_b, md);
+  if (n == "merger.mlp.2.weight") return W(&t->fc2_w, oh, md, md);
+  if (n == "merger.mlp.2.bias") return V(&t->fc2_b, oh);
+  if (n.rfind("blocks.", 0) == 0) {
+    const size_t dot = n.find('.', 7);
+    if (dot == std::string::npos) return fail(VR2_ERR_ARG, "vr2_tower_set_weight: cannot parse '%s'", name);
+    const int l = atoi(n.substr(7, dot - 7).c_str());
+    if (l < 0 || l >= t->cfg.depth) return fail(VR2_ERR_ARG, "vr2_tower_set_weight: layer %d out of range in '%s'", l, name);
+    Layer& L = t->layers[l];
+    const std::string k = n.substr(dot + 1);
+    if (k == "norm1.weight") return V(&L.norm1_w, h);
+    if (k == "norm2.weight") return V(&L.norm2_w, h);
+    if (k == "attn.qkv.weight") return W(&L.qkv_w, 3 * h, h, h);
+    if (k == "attn.qkv.bias") return V(&L.qkv_b, 3 * h);
+    if (k == "attn.proj.weight") return W(&L.proj_w, h, h, h);
+    if (k == "attn.proj.bias") return V(&L.proj_b, h);
+    // gate rows g -> tile (g/128), columns [0,128); up rows u -> same tile, columns [128,256)
+    if (k == "mlp.gate_proj.weight") { int rc = mat(&L.gu_w, true, inter, h, h, 128, 256, 0); L.gate_w_set = rc == VR2_OK; return rc; }
+    if (k == "mlp.up_proj.weight") { int rc = mat(&L.gu_w, true, inter, h, h, 128, 256, 128); L.up_w_set = rc == VR2_OK; return rc; }
+    if (k == "mlp.gate_proj.bias") { int rc = mat(&L.gu_b, false, inter, 1, 1, 128, 256, 0); L.gate_b_set = rc == VR2_OK; return rc; }
+    if (k == "mlp.up_proj.bias") { int rc = mat(&L.gu_b, false, inter, 1, 1, 128, 256, 128); L.up_b_set = rc == VR2_OK; return rc; }
+    if (k == "mlp.down_proj.weight") return W(&L.down_w, h, inter, ip);  // K padded with zeros to ipad
+    if (k == "mlp.down_proj.bias") return V(&L.down_b, h);
+  }
+  return fail(VR2_ERR_ARG, "vr2_tower_set_weight: unknown tensor '%s'", name);
+}
+
+extern "C" int vr2_tower_finalize(vr2_tower* t) {
+  if (t == nullptr) return fail(VR2_ERR_ARG, "vr2_tower_finalize: null tower");
+  std::string missing;
+  auto need = [&](bool ok, const std::string& nm) { if (!ok) missing += (missing.empty() ? "" : ", ") + nm; };
+  need(t->patch_w.set, "patch_embed.proj.weight");
+  need(t->lnq_w.set, "merger.ln_q.weight");
+  need(t->fc1_w.set, "merger.mlp.0.weight");
+  need(t->fc1_b.set, "merger.mlp.0.bias");
+  need(t->fc2_w.set, "merger.mlp.2.weight");
+  need(t->fc2_b.set, "merger.mlp.2.bias");
+  for (int l = 0; l < t->cfg.depth; ++l) {
+    Layer& L = t->layers[l];
+    const std::string p = "blocks." + std::to_string(l) + ".";
+    need(L.norm1_w.set, p + "norm1.weight");
+    need(L.norm2_w.set, p + "norm2.weight");
+    need(L.qkv_w.set, p + "attn.qkv.weight");
+    need(L.qkv_b.set, p + "attn.qkv.bias");
+    need(L.proj_w.set, p + "attn.proj.weight");
+    need(L.proj_b.set, p + "attn.proj.bias");
+    need(L.gate_w_set, p + "mlp.gate_proj.weight");
+    need(L.up_w_set, p + "mlp.up_proj.weight");
+    need(L.gate_b_set, p + "mlp.gate_proj.bias");
+    need(L.up_b_set, p + "mlp.up_proj.bias");
+    need(L.down_w.set, p + "mlp.down_proj.weight");
+    need(L.down_b.set, p + "mlp.down_proj.bias");
+  }
+  if (!missing.empty()) {
+    if (missing.size() > 600) missing = missing.substr(0, 600) + " ...";
+    return fail(VR2_ERR_STATE, "vr2_tower_finalize: missing tensors: %s", missing.c_str());
+  }
+  t->finalized = true;
+  return VR2_OK;
+}
+
+namespace {
+
+struct Workspace {
+  float* x;
+  __nv_bfloat16* xb;
+  __nv_bfloat16* qkv;   // also the merger's normalised input [N/4, 4h]
+  __nv_bfloat16* att;
+  __nv_bfloat16* hbuf;  // also the merger's hidden [N/4, 4h]
+  float* ssq;
+  __nv_bfloat16* pix;
+  size_t bytes;
+};
+
+Workspace carve_ws(const vr2_tower* t, int64_t n, void* base) {
+  auto rnd = [](size_t b) { return (b + 1023) & ~static_cast<size_t>(1023); };
+  const size_t h = t->cfg.hidden_size, N = static_cast<size_t>(n);
+  char* cur = static_cast<char*>(base);
+  Workspace w;
+  auto take = [&](size_t bytes) { char* p = cur; cur += rnd(bytes); return p; };
+  w.x = reinterpret_cast<float*>(take(N * h * 4));
+  w.xb = reinterpret_cast<__nv_bfloat16*>(take(N * h * 2));
+  w.qkv = reinterpret_cast<__nv_bfloat16*>(take(N * 3 * h * 2));
+  w.att = reinterpret_cast<__nv_bfloat16*>(take(N * h * 2));
+  w.hbuf = reinterpret_cast<__nv_bfloat16*>(take(N * std::max<size_t>(t->ipad, h) * 2));
+  w.ssq = reinterpret_cast<float*>(take(N * (h / 256) * 4));
+  w.pix = reinterpret_cast<__nv_bfloat16*>(take(N * t->patch_k * 2));
+  w.bytes = static_cast<size_t>(cur - static_cast<char*>(base));
+  return w;
+}
+
+}  // namespace
+
+extern "C" size_t vr2_tower_workspace_bytes(const vr2_tower* t, int64_t n_patches) {
+  if (t == nullptr || n_patches <= 0) return 0;
+  return carve_ws(t, n_patches, nullptr).bytes;
+}
+
+extern "C" int64_t vr2_tower_launch_count(const vr2_tower* t, const vr2_plan* plan, int32_t pixels_dtype) {
+  if (t == nullptr || plan == nullptr) return -1;
+  return (pixels_dtype == VR2_F32 ? 1 : 0) + 1 + 5 * static_cast<int64_t>(t->cfg.depth) + 3;
+}
+
+extern "C" int vr2_tower_forward(vr2_tower* t, const vr2_plan* plan, const void* pixels, int32_t pixels_dtype,
+                                 void* out, int32_t out_dtype, void* workspace, size_t workspace_bytes,
+                                 void* stream_v) {
+  if (t == nullptr || plan == nullptr || pixels == nullptr || out == nullptr || workspace == nullptr)
+    return fail(VR2_ERR_ARG, "vr2_tower_forward: null argument");
+  if (!t->finalized) return fail(VR2_ERR_STATE, "vr2_tower_forward: weights not finalized");
+  if (pixels_dtype != VR2_F32 && pixels_dtype != VR2_BF16) return fail(VR2_ERR_ARG, "vr2_tower_forward: pixels dtype %d unsupported", pixels_dtype);
+  if (out_dtype != VR2_F32 && out_dtype != VR2_BF16) return fail(VR2_ERR_ARG, "vr2_tower_forward: out dtype %d unsupported", out_dtype);
+  if (plan->half_dim * 2 != t->head_dim || plan->merge != t->cfg.spatial_merge_size)
+    return fail(VR2_ERR_STATE, "vr2_tower_forward: plan was built for a different head_dim / merge size");
+  if (reinterpret_cast<uintptr_t>(workspace) & 1023) return fail(VR2_ERR_ARG, "vr2_tower_forward: workspace must be 1024-byte aligned");
+  if ((reinterpret_cast<uintptr_t>(pixels) & 15) || (reinterpret_cast<uintptr_t>(out) & 15))
+    return fail(VR2_ERR_ARG, "vr2_tower_forward: pixels/out must be 16-byte aligned");
+  const int64_t N = plan->n_patches;
+  const Workspace w = carve_ws(t, N, workspace);
+  if (w.bytes > workspace_bytes)
+    return fail(VR2_ERR_ARG, "vr2_tower_forward: workspace %zu < required %zu bytes", workspace_bytes, w.bytes);
+  cudaStream_t s = as_stream(stream_v);
+  const int h = t->cfg.hidden_size;
+  const int parts = h / 256;
+  const float eps = t->cfg.rms_norm_eps;
+  const char* msg = "";
+  auto G = [&](const GemmArgs& a, const char* what) -> int {
+    cudaError_t e = gemm_launch(a, t->num_sms, s, &msg);
+    if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? VR2_ERR_ARG : VR2_ERR_CUDA, "vr2_tower_forward: %s: %s %s", what, cudaGetErrorString(e), msg);
+    return VR2_OK;
+  };
+  int rc;
+
+  // ---- patch embed (Conv3d with kernel == stride == a [N,1176] x [1176,1280] GEMM), stored window-permuted
+  const __nv_bfloat16* pix = static_cast<const __nv_bfloat16*>(pixels);
+  if (pixels_dtype == VR2_F32) {
+    VR2_CUDA(cast_f32_to_bf16(static_cast<const float*>(pixels), w.pix, N * t->patch_k, s));
+    pix = w.pix;
+  }
+  {
+    GemmArgs a{};
+    a.A = pix; a.lda = t->patch_k; a.W = static_cast<const __nv_bfloat16*>(t->patch_w.ptr); a.ldw = t->patch_k;
+    a.M = static_cast<int>(N); a.N = h; a.K = t->patch_k;
+    a.epilogue = EPI_RESID; a.flags = 0;
+    a.x = w.x; a.ldx = h; a.out_bf16 = w.xb; a.ld_out = h;
+    a.row_map = plan->row_map;
+    a.norm_w = static_cast<const float*>(t->layers[0].norm1_w.ptr);
+    a.ssq = w.ssq;
+    if ((rc = G(a, "patch_embed")) != VR2_OK) return rc;
+  }
+
+  for (int l = 0; l < t->cfg.depth; ++l) {
+    const Layer& L = t->layers[l];
+    {
+      GemmArgs a{};
+      a.A = w.xb; a.lda = h; a.W = static_cast<const __nv_bfloat16*>(L.qkv_w.ptr); a.ldw = h;
+      a.M = static_cast<int>(N); a.N = 3 * h; a.K = h;
+      a.epilogue = EPI_QKV;
+      a.bias = static_cast<const float*>(L.qkv_b.ptr);
+      a.out_bf16 = w.qkv; a.ld_out = 3 * h;
+      a.ssq_in = w.ssq; a.ssq_parts = parts; a.inv_dim = 1.0f / h; a.eps = eps;
+      a.cos_tab = plan->cos_tab; a.sin_tab = plan->sin_tab;
+      if ((rc = G(a, "qkv")) != VR2_OK) return rc;
+    }
+    {
+      const bool full = is_full_layer(t, l);
+      VR2_CUDA(attention_launch(w.qkv, w.att, full ? plan->tiles_full : plan->tiles_window,
+                                static_cast<int>(full ? plan->n_tiles_full : plan->n_tiles_window), t->cfg.num_heads,
+                                3 * h, h, s));
+    }
+    {
+      GemmArgs a{};
+      a.A = w.att; a.lda = h; a.W = static_cast<const __nv_bfloat16*>(L.proj_w.ptr); a.ldw = h;
+      a.M = static_cast<int>(N); a.N = h; a.K = h;
+      a.epilogue = EPI_RESID; a.flags = GEMM_ADD_RESID;
+      a.bias = static_cast<const float*>(L.proj_b.ptr);
+      a.x = w.x; a.ldx = h; a.out_bf16 = w.xb; a.ld_out = h;
+      a.norm_w = static_cast<const float*>(L.norm2_w.ptr);
+      a.ssq = w.ssq;
+      if ((rc = G(a, "proj")) != VR2_OK) return rc;
+    }
+    {
+      GemmArgs a{};
+      a.A = w.xb; a.lda = h; a.W = static_cast<const __nv_bfloat16*>(L.gu_w.ptr); a.ldw = h;
+      a.M = static_cast<int>(N); a.N = 2 * t->ipad; a.K = h;
+      a.epilogue = EPI_SWIGLU;
+      a.bias = static_cast<const float*>(L.gu_b.ptr);
+      a.out_bf16 = w.hbuf; a.ld_out = t->ipad;
+      a.ssq_in = w.ssq; a.ssq_parts = parts; a.inv_dim = 1.0f / h; a.eps = eps;
+      if ((rc = G(a, "gate_up")) != VR2_OK) return rc;
+    }
+    {
+      GemmArgs a{};
+      a.A = w.hbuf; a.lda = t->ipad; a.W = static_cast<const __nv_bfloat16*>(L.down_w.ptr); a.ldw = t->ipad;
+      a.M = static_cast<int>(N); a.N = h; a.K = t->ipad;
+      a.epilogue = EPI_RESID; a.flags = GEMM_ADD_RESID;
+      a.bias = static_cast<const float*>(L.down_b.ptr);
+      a.x = w.x; a.ldx = h; a.out_bf16 = w.xb; a.ld_out = h;
+      a.norm_w = static_cast<const float*>(l + 1 < t->cfg.depth ? t->layers[l + 1].norm1_w.ptr : t->lnq_w.ptr);
+      a.ssq = w.ssq;
+      if ((rc = G(a, "down")) != VR2_OK) return rc;
+    }
+  }
+
+  // ---- PatchMerger: ln_q per patch row, then 4 consecutive window-order rows form one merged token
+  const int64_t T = plan->n_tokens;
+  const int md = t->merge_dim;
+  VR2_CUDA(rmsnorm_to_bf16(w.x, static_cast<const float*>(t->lnq_w.ptr), w.qkv, N, h, eps, s));
+  {
+    GemmArgs a{};
+    a.A = w.qkv; a.lda = md; a.W = static_cast<const __nv_bfloat16*>(t->fc1_w.ptr); a.ldw = md;
+    a.M = static_cast<int>(T); a.N = md; a.K = md;
+    a.epilogue = EPI_STORE; a.flags = GEMM_GELU;
+    a.bias = static_cast<const float*>(t->fc1_b.ptr);
+    a.out_bf16 = w.hbuf; a.ld_out = md;
+    if ((rc = G(a, "merger.fc1")) != VR2_OK) return rc;
+  }
+  {
+    GemmArgs a{};
+    a.A = w.hbuf; a.lda = md; a.W = static_cast<const __nv_bfloat16*>(t->fc2_w.ptr); a.ldw = md;
+    a.M = static_cast<int>(T); a.N = t->cfg.out_hidden_size; a.K = md;
+    a.epilogue = EPI_STORE; a.flags = out_dtype == VR2_F32 ? GEMM_OUT_F32 : 0;
+    a.bias = static_cast<const float*>(t->fc2_b.ptr);
+    a.out_bf16 = static_cast<__nv_bfloat16*>(out); a.out_f32 = static_cast<float*>(out);
+    a.ld_out = t->cfg.out_hidden_size;
+    a.row_map = plan->out_map;  // inverse window permute fused into the store (HF :512-513)
+    if ((rc = G(a, "merger.fc2")) != VR2_OK) return rc;
+  }
+  return VR2_OK;
+}
+
+// ----------------------------------------------------------------- single operators (test surface)
+extern "C" int vr2_op_linear(const void* a_dev, const void* w_dev, const float* bias, void* out, int32_t out_dtype,
+                             int32_t M, int32_t N, int32_t K, int32_t gelu, void* stream_v) {
+  if (a_dev == nullptr || w_dev == nullptr || out == nullptr) return fail(VR2_ERR_ARG, "vr2_op_linear: null pointer");
+  if (out_dtype != VR2_F32 && out_dtype != VR2_BF16) return fail(VR2_ERR_ARG, "vr2_op_linear: out dtype");
+  if (K % 8 != 0) return fail(VR2_ERR_ARG, "vr2_op_linear: K %% 8 != 0 (rows must be 16-byte aligned)");
+  int dev = 0, sms = 148;
+  VR2_CUDA(cudaGetDevice(&dev));
+  VR2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  GemmArgs a{};
+  a.A = static_cast<const __nv_bfloat16*>(a_dev); a.lda = K;
+  a.W = static_cast<const __nv_bfloat16*>(w_dev); a.ldw = K;
+  a.M = M; a.N = N; a.K = K;
+  a.epilogue = EPI_STORE;
+  a.flags = (gelu ? GEMM_GELU : 0) | (out_dtype == VR2_F32 ? GEMM_OUT_F32 : 0);
+  a.bias = bias;
+  a.out_bf16 = static_cast<__nv_bfloat16*>(out); a.out_f32 = static_cast<float*>(out); a.ld_out = N;
+  const char* msg = "";
+  cudaError_t e = gemm_launch(a, sms, as_stream(stream_v), &msg);
+  if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? VR2_ERR_ARG : VR2_ERR_CUDA, "vr2_op_linear: %s %s", cudaGetErrorString(e), msg);
+  return VR2_OK;
+}
+
+extern "C" int vr2_op_rmsnorm(const float* x, const float* w, void* out, int64_t rows, int32_t dim, float eps,
+                              void* stream_v) {
+  if (x == nullptr || w == nullptr || out == nullptr) return fail(VR2_ERR_ARG, "vr2_op_rmsnorm: null pointer");
+  if (dim % 4 != 0) return fail(VR2_ERR_ARG, "vr2_op_rmsnorm: dim %% 4 != 0");
+  VR2_CUDA(rmsnorm_to_bf16(x, w, static_cast<__nv_bfloat16*>(out), rows, dim, eps, as_stream(stream_v)));
+  return VR2_OK;
+}
+
+extern "C" int vr2_op_attention(const void* qkv, void* out, const int32_t* cu, int32_t n_seq, int32_t num_heads,
+                                void* stream_v) {
+  if (qkv == nullptr || out == nullptr || cu == nullptr || n_seq <= 0) return fail(VR2_ERR_ARG, "vr2_op_attention: null pointer");
+  std::vector<int4> tiles;
+  for (int i = 0; i < n_seq; ++i) {
+    const int s0 = cu[i], L = cu[i + 1] - cu[i];
+    if (L < 0) return fail(VR2_ERR_ARG, "vr2_op_attention: cu_seqlens not monotone");
+    for (int q0 = 0; q0 < L; q0 += 64) tiles.push_back(make_int4(s0 + q0, std::min(64, L - q0), s0, L));
+  }
+  if (tiles.empty()) return VR2_OK;
+  cudaStream_t s = as_stream(stream_v);
+  int4* d = nullptr;
+  VR2_CUDA(cudaMalloc(&d, tiles.size() * 16));
+  cudaError_t e = cudaMemcpyAsync(d, tiles.data(), tiles.size() * 16, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess)
+    e = attention_launch(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), d,
+                         static_cast<int>(tiles.size()), num_heads, 3 * num_heads * 80, num_heads * 80, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(VR2_ERR_CUDA, "vr2_op_attention: %s", cudaGetErrorString(e));
+  return VR2_OK;
+}

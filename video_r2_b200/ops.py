@@ -1,0 +1,52 @@
+"""Single-kernel entry points of libvr2.so (the vr2_op_* functions of include/vr2.h), exposed
+so tests can pin each kernel against the oracle.  Not a general operator library."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from ._lib import VR2_BF16, VR2_F32, check, lib
+
+
+def _s(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def linear(a: torch.Tensor, w: torch.Tensor, bias=None, gelu: bool = False, out_dtype=torch.float32) -> torch.Tensor:
+    """a [M,K] bf16, w [N,K] bf16 -> act(a @ w.T + bias), tcgen05 GEMM with fp32 accumulation."""
+    assert a.is_cuda and a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    a, w = a.contiguous(), w.contiguous()
+    M, K = a.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+    b = bias.to(torch.float32).contiguous() if bias is not None else None
+    with torch.cuda.device(a.device):
+        check(lib().vr2_op_linear(a.data_ptr(), w.data_ptr(), b.data_ptr() if b is not None else None, out.data_ptr(),
+                                  VR2_F32 if out_dtype == torch.float32 else VR2_BF16, M, N, K, int(gelu), _s(a)),
+              "vr2_op_linear")
+    return out
+
+
+def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    """x fp32 [rows, dim] -> bf16(x * rsqrt(mean(x^2)+eps) * w)."""
+    assert x.is_cuda and x.dtype == torch.float32
+    x = x.contiguous()
+    out = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib().vr2_op_rmsnorm(x.data_ptr(), w.to(torch.float32).contiguous().data_ptr(), out.data_ptr(),
+                                   x.shape[0], x.shape[1], eps, _s(x)), "vr2_op_rmsnorm")
+    return out
+
+
+def attention(qkv: torch.Tensor, cu_seqlens, num_heads: int) -> torch.Tensor:
+    """qkv bf16 [N, 3*heads*80] (q | k | v), cu_seqlens int list/tensor -> bf16 [N, heads*80]."""
+    assert qkv.is_cuda and qkv.dtype == torch.bfloat16
+    qkv = qkv.contiguous()
+    cu = [int(v) for v in (cu_seqlens.tolist() if isinstance(cu_seqlens, torch.Tensor) else cu_seqlens)]
+    arr = (C.c_int32 * len(cu))(*cu)
+    out = torch.empty((qkv.shape[0], num_heads * 80), dtype=torch.bfloat16, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        check(lib().vr2_op_attention(qkv.data_ptr(), out.data_ptr(), arr, len(cu) - 1, num_heads, _s(qkv)),
+              "vr2_op_attention")
+    return out

@@ -1,0 +1,259 @@
+"""Host-side mirror of `Qwen2_5_VisionTransformerPretrainedModel` (transformers
+modeling_qwen2_5_vl.py:345-518) over the C ABI in include/vr2.h.
+
+PyTorch is used for device memory, streams and nothing else: every kernel is in
+libvr2.so.  `VisionTower.forward(hidden_states, grid_thw)` keeps the 4.51.1
+contract Video-R2 relies on (train/src/train/monkey_patch_forward.py:392): a
+plain tensor `[N/4, out_hidden]`, same dtype as the input, original token order.
+"""
+from __future__ import annotations
+
+import collections
+import ctypes as C
+import dataclasses
+
+import torch
+
+from . import _lib
+from ._lib import VR2_BF16, VR2_F32, check, lib
+
+
+@dataclasses.dataclass(frozen=True)
+class VisionConfig:
+    """Qwen2.5-VL-7B vision_config.  Set explicitly: the HF class defaults differ
+    (hidden_size 3584, tokens_per_second 4)."""
+    depth: int = 32
+    hidden_size: int = 1280
+    num_heads: int = 16
+    intermediate_size: int = 3420
+    out_hidden_size: int = 3584
+    patch_size: int = 14
+    temporal_patch_size: int = 2
+    in_channels: int = 3
+    spatial_merge_size: int = 2
+    window_size: int = 112
+    fullatt_block_indexes: tuple = (7, 15, 23, 31)
+    rms_norm_eps: float = 1e-6
+    rope_theta: float = 10000.0
+    tokens_per_second: float = 2
+
+    @classmethod
+    def from_hf(cls, hf_cfg):
+        get = lambda k, d: getattr(hf_cfg, k, d)
+        return cls(
+            depth=hf_cfg.depth, hidden_size=hf_cfg.hidden_size, num_heads=hf_cfg.num_heads,
+            intermediate_size=hf_cfg.intermediate_size, out_hidden_size=hf_cfg.out_hidden_size,
+            patch_size=hf_cfg.patch_size, temporal_patch_size=get("temporal_patch_size", 2),
+            in_channels=get("in_channels", get("in_chans", 3)), spatial_merge_size=hf_cfg.spatial_merge_size,
+            window_size=hf_cfg.window_size, fullatt_block_indexes=tuple(hf_cfg.fullatt_block_indexes),
+            rms_norm_eps=1e-6, rope_theta=10000.0, tokens_per_second=get("tokens_per_second", 2),
+        )
+
+    @property
+    def patch_dim(self):
+        return self.in_channels * self.temporal_patch_size * self.patch_size * self.patch_size
+
+    @property
+    def head_dim(self):
+        return self.hidden_size // self.num_heads
+
+
+def _dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return VR2_F32
+    if dt == torch.bfloat16:
+        return VR2_BF16
+    raise ValueError(f"unsupported dtype {dt}: the tower takes float32 or bfloat16")
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class Plan:
+    """All index tables derived from grid_thw (window index, inverse, cu_seqlens,
+    rotary tables, attention tile schedule), built on the device once per distinct grid."""
+
+    def __init__(self, cfg: VisionConfig, grid_thw, device):
+        if isinstance(grid_thw, torch.Tensor):
+            grid = grid_thw.detach().to("cpu", torch.int64).reshape(-1, 3).tolist()  # one small D2H, as HF's .tolist()
+        else:
+            grid = [[int(v) for v in row] for row in grid_thw]
+        if len(grid) == 0:
+            raise ValueError("grid_thw is empty")
+        self.grid = tuple(tuple(r) for r in grid)
+        self.device = torch.device(device)
+        flat = (C.c_int64 * (3 * len(grid)))(*[v for row in grid for v in row])
+        pc = _lib.PlanConfig(cfg.spatial_merge_size, cfg.window_size, cfg.patch_size, cfg.head_dim, cfg.rope_theta)
+        handle = C.c_void_p()
+        with torch.cuda.device(self.device):
+            check(lib().vr2_plan_create(C.byref(pc), flat, len(grid), _stream_ptr(self.device), C.byref(handle)),
+                  "vr2_plan_create")
+        self._h = handle
+        self.half_dim = cfg.head_dim // 2
+        self.num_patches = lib().vr2_plan_num_patches(handle)
+        self.num_tokens = lib().vr2_plan_num_tokens(handle)
+        self.num_windows = lib().vr2_plan_num_windows(handle)
+        self.num_slices = lib().vr2_plan_num_slices(handle)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                lib().vr2_plan_destroy(h)
+            except Exception:
+                pass
+
+    def export(self):
+        """-> dict of torch tensors (device): window_index, reverse_index, cu_window_seqlens,
+        cu_seqlens, pos_hw — the bit-exact counterparts of HF's helpers."""
+        d = self.device
+        out = {
+            "window_index": torch.empty(self.num_tokens, dtype=torch.int64, device=d),
+            "reverse_index": torch.empty(self.num_tokens, dtype=torch.int64, device=d),
+            "cu_window_seqlens": torch.empty(self.num_windows + 1, dtype=torch.int32, device=d),
+            "cu_seqlens": torch.empty(self.num_slices + 1, dtype=torch.int32, device=d),
+            "pos_hw": torch.empty(self.num_patches, 2, dtype=torch.int32, device=d),
+        }
+        with torch.cuda.device(d):
+            check(lib().vr2_plan_export(self._h, out["window_index"].data_ptr(), out["reverse_index"].data_ptr(),
+                                        out["cu_window_seqlens"].data_ptr(), out["cu_seqlens"].data_ptr(),
+                                        out["pos_hw"].data_ptr(), _stream_ptr(d)), "vr2_plan_export")
+        return out
+
+    def export_rotary(self):
+        d = self.device
+        cos = torch.empty(self.num_patches, self.half_dim, dtype=torch.float32, device=d)
+        sin = torch.empty_like(cos)
+        with torch.cuda.device(d):
+            check(lib().vr2_plan_export_rotary(self._h, cos.data_ptr(), sin.data_ptr(), _stream_ptr(d)),
+                  "vr2_plan_export_rotary")
+        return cos, sin
+
+
+def gather_rows(src: torch.Tensor, index: torch.Tensor) -> torch.Tensor:
+    """dst[i] = src[index[i]] for a 2-D contiguous src — the window permute / inverse as a
+    bit-exact HBM gather (HF :478-484, :512-513)."""
+    if src.dim() != 2 or not src.is_contiguous() or not src.is_cuda:
+        raise ValueError("gather_rows: src must be a contiguous 2-D CUDA tensor")
+    index = index.to(device=src.device, dtype=torch.int64).contiguous()
+    row_bytes = src.shape[1] * src.element_size()
+    dst = torch.empty((index.numel(), src.shape[1]), dtype=src.dtype, device=src.device)
+    with torch.cuda.device(src.device):
+        check(lib().vr2_gather_rows(src.data_ptr(), dst.data_ptr(), index.data_ptr(), index.numel(), src.shape[0],
+                                    row_bytes, _stream_ptr(src.device)), "vr2_gather_rows")
+    return dst
+
+
+class VisionTower:
+    """Owns a vr2_tower handle and its repacked weights.
+
+    state_dict: name -> tensor with the HF vision-module names
+    ("patch_embed.proj.weight", "blocks.0.attn.qkv.weight", ...), fp32 or bf16, any device."""
+
+    def __init__(self, cfg: VisionConfig, state_dict, device="cuda:0", plan_cache: int = 16):
+        self.cfg = cfg
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.Vr2Error("VisionTower needs a CUDA device: there is no CPU path")
+        tc = _lib.TowerConfig()
+        for f in ("depth", "hidden_size", "num_heads", "intermediate_size", "out_hidden_size", "patch_size",
+                  "temporal_patch_size", "in_channels", "spatial_merge_size", "window_size"):
+            setattr(tc, f, int(getattr(cfg, f)))
+        full = list(cfg.fullatt_block_indexes)
+        if len(full) > 8:
+            raise ValueError("at most 8 full-attention layers")
+        tc.n_fullatt = len(full)
+        for i, v in enumerate(full):
+            tc.fullatt_block_indexes[i] = int(v)
+        tc.rms_norm_eps = cfg.rms_norm_eps
+        tc.rope_theta = cfg.rope_theta
+        handle = C.c_void_p()
+        index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        check(lib().vr2_tower_create(C.byref(tc), index, C.byref(handle)), "vr2_tower_create")
+        self._h = handle
+        self._plans = collections.OrderedDict()
+        self._plan_cache = plan_cache
+        self._ws = None
+        self.load_state_dict(state_dict)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                lib().vr2_tower_destroy(h)
+            except Exception:
+                pass
+
+    def load_state_dict(self, state_dict):
+        s = _stream_ptr(self.device)
+        with torch.cuda.device(self.device):
+            for name, t in state_dict.items():
+                if name.endswith("inv_freq"):
+                    continue  # the library owns its fp32 rotary tables (train_sft.py:46 casts buffers to bf16)
+                src = t.detach()
+                if src.dtype not in (torch.float32, torch.bfloat16):
+                    src = src.float()
+                src = src.to(self.device).contiguous()
+                shape = (C.c_int64 * max(src.dim(), 1))(*(src.shape if src.dim() else (1,)))
+                check(lib().vr2_tower_set_weight(self._h, name.encode(), src.data_ptr(), _dtype_code(src.dtype), shape,
+                                                 max(src.dim(), 1), s), f"vr2_tower_set_weight({name})")
+                torch.cuda.current_stream(self.device).synchronize()  # src may be a temporary
+            check(lib().vr2_tower_finalize(self._h), "vr2_tower_finalize")
+
+    # ------------------------------------------------------------------ plans / workspace
+    def plan(self, grid_thw) -> Plan:
+        if isinstance(grid_thw, Plan):
+            return grid_thw
+        if isinstance(grid_thw, torch.Tensor):
+            key = tuple(grid_thw.detach().to("cpu", torch.int64).reshape(-1).tolist())
+        else:
+            key = tuple(int(v) for row in grid_thw for v in row)
+        p = self._plans.get(key)
+        if p is None:
+            p = Plan(self.cfg, [key[i:i + 3] for i in range(0, len(key), 3)], self.device)
+            self._plans[key] = p
+            while len(self._plans) > self._plan_cache:
+                self._plans.popitem(last=False)
+        else:
+            self._plans.move_to_end(key)
+        return p
+
+    def _workspace(self, n_patches: int) -> torch.Tensor:
+        need = lib().vr2_tower_workspace_bytes(self._h, n_patches)
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    # ------------------------------------------------------------------ forward
+    @torch.no_grad()
+    def forward(self, hidden_states: torch.Tensor, grid_thw, out_dtype=None, out=None) -> torch.Tensor:
+        """hidden_states: [N, 1176] fp32/bf16 on this tower's device.  Returns [N/4, out_hidden]."""
+        plan = self.plan(grid_thw)
+        x = hidden_states
+        if x.device != self.device:
+            x = x.to(self.device, non_blocking=True)
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.to(torch.bfloat16)
+        x = x.contiguous()
+        if x.dim() != 2 or x.shape[1] != self.cfg.patch_dim:
+            raise ValueError(f"hidden_states must be [N, {self.cfg.patch_dim}], got {tuple(x.shape)}")
+        if x.shape[0] != plan.num_patches:
+            raise ValueError(f"hidden_states has {x.shape[0]} rows but grid_thw describes {plan.num_patches} patches")
+        odt = out_dtype or x.dtype
+        if out is None:
+            out = torch.empty((plan.num_tokens, self.cfg.out_hidden_size), dtype=odt, device=self.device)
+        ws = self._workspace(plan.num_patches)
+        base = ws.data_ptr()
+        aligned = (base + 1023) & ~1023
+        with torch.cuda.device(self.device):
+            check(lib().vr2_tower_forward(self._h, plan._h, x.data_ptr(), _dtype_code(x.dtype), out.data_ptr(),
+                                          _dtype_code(out.dtype), aligned, ws.numel() - (aligned - base),
+                                          _stream_ptr(self.device)), "vr2_tower_forward")
+        return out
+
+    __call__ = forward
+
+    def launch_count(self, grid_thw, dtype=torch.bfloat16) -> int:
+        return int(lib().vr2_tower_launch_count(self._h, self.plan(grid_thw)._h, _dtype_code(dtype)))
