@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""Benchmark of the Video-R2 hot path on B200: Qwen2.5-VL-7B vision tower + get_rope_index.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl vr2|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one pass of the hot path over one batch: every rank encodes its share of the batch's
+temporal slices (N=1: the whole clip), the merged embeddings are all-gathered (N>1), and the
+M-RoPE position ids of the batch are computed.  Workload at N=1 is BASELINE.json configs[1]
+("Video-R2 eval setting": one 32-frame 448x448 clip, grid_thw [16,32,32], 16384 patches -> 4096
+visual tokens, bf16); at N GPUs the batch is N such clips (weak scaling), sharded by slice.
+
+Prints ONE JSON line (rank 0).  `value` = visual tokens/s of the whole job with inputs resident in
+HBM; `e2e` = the same through the public API from pinned HOST buffers (H2D of the pixels and D2H
+of the embeddings + position ids inside the timed region).  `--impl reference` times the
+reference's own implementation (the Hugging Face module Video-R2 calls) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "visual_tokens_per_sec"
+UNIT = "tokens/s"
+CLIP = (16, 32, 32)          # configs[1]: 32 frames at 448x448 -> t=16 temporal slices of 32x32 patches
+TEXT_BEFORE, TEXT_AFTER = 32, 64
+FLOP_PER_TOKEN = 5.261e9     # BASELINE.md §3 (dense layers + attention, algorithmic)
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p, "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.05):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop.is_set():
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the HF module Video-R2 executes, on the host cores
+# ---------------------------------------------------------------------------------------------
+def build_hf_reference():
+    import torch
+    from transformers.models.qwen2_5_vl.configuration_qwen2_5_vl import Qwen2_5_VLVisionConfig
+    from transformers.models.qwen2_5_vl.modeling_qwen2_5_vl import Qwen2_5_VisionTransformerPretrainedModel as V
+
+    cfg = Qwen2_5_VLVisionConfig(depth=32, hidden_size=1280, intermediate_size=3420, num_heads=16,
+                                 out_hidden_size=3584, patch_size=14, spatial_merge_size=2, temporal_patch_size=2,
+                                 window_size=112, fullatt_block_indexes=[7, 15, 23, 31], tokens_per_second=2,
+                                 hidden_act="silu")
+    cfg._attn_implementation = "sdpa"
+    with torch.device("meta"):
+        m = V._from_config(cfg)
+    m = m.to_empty(device="cpu")
+    g = torch.Generator().manual_seed(0)
+    for p in m.parameters():
+        p.data.normal_(0, 0.02, generator=g)
+    m.rotary_pos_emb.inv_freq = 1.0 / (10000.0 ** (torch.arange(0, 40, 2, dtype=torch.float) / 40))
+    return m.eval()
+
+
+def cpu_reference_runner():
+    """-> (kind, fn(slices) -> seconds for one forward over [[slices,32,32]] + rope index of that sample)."""
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    from oracle import rope_index as orope
+    try:
+        model = build_hf_reference()
+        kind = "reference"
+
+        def tower(x, grid):
+            with torch.no_grad():
+                r = model(x, grid_thw=torch.tensor(grid))
+            return r.pooler_output if hasattr(r, "pooler_output") else r
+    except Exception as e:  # transformers missing: time the oracle port instead
+        print(f"[bench] HF reference unavailable ({e!r}); timing the oracle port", file=sys.stderr)
+        from oracle import tower as otower
+        ocfg = otower.TowerConfig()
+        w = otower.make_weights(ocfg, seed=0, bf16_exact=False)
+        kind = "port"
+
+        def tower(x, grid):
+            return otower.tower_forward(w, ocfg, x, grid)
+
+    def run(slices: int) -> float:
+        grid = [[slices, CLIP[1], CLIP[2]]]
+        n = slices * CLIP[1] * CLIP[2]
+        x = torch.randn(n, 1176, generator=torch.Generator().manual_seed(1))
+        ids = torch.tensor([[1000] * TEXT_BEFORE + [151652] + [151656] * (n // 4) + [151653] + [1000] * TEXT_AFTER])
+        t0 = time.perf_counter()
+        out = tower(x, grid)
+        orope.get_rope_index(ids, None, torch.tensor(grid), torch.tensor([1.0]), None)
+        dt = time.perf_counter() - t0
+        assert out.shape[0] == n // 4
+        return dt
+
+    return kind, run
+
+
+def run_reference(args, rank):
+    import torch
+    if rank != 0:
+        return
+    kind, run = cpu_reference_runner()
+    t1 = run(1)  # also the first warm-up
+    budget = 150.0
+    slices = max(1, min(CLIP[0], int(budget / max(1e-3, (args.steps + args.warmup) * t1))))
+    for _ in range(max(0, args.warmup - 1)):
+        run(slices)
+    times = [run(slices) for _ in range(args.steps)]
+    dt = sum(times) / len(times)
+    tokens = slices * CLIP[1] * CLIP[2] // 4
+    value = tokens / dt
+    cores = torch.get_num_threads()
+    sample = f"{slices} of the {CLIP[0]} temporal slices of the config-2 clip per step ({tokens} tokens), fp32, sdpa"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "Video-R2 eval setting: 32-frame 448x448 clip, grid_thw [16,32,32], + get_rope_index",
+                   "sample": sample, "reference": "transformers Qwen2_5_VisionTransformerPretrainedModel on host CPU"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# own arm
+# ---------------------------------------------------------------------------------------------
+def synth_state_dict(cfg, device, seed=0):
+    """Random-init weights of the named architecture, generated on the device (bf16)."""
+    import torch
+    from oracle.tower import TowerConfig, weight_shapes
+    g = torch.Generator(device=device).manual_seed(seed)
+    sd = {}
+    for name, shape in weight_shapes(TowerConfig(depth=cfg.depth)).items():
+        if name.endswith("norm1.weight") or name.endswith("norm2.weight") or name.endswith("ln_q.weight"):
+            t = 1.0 + 0.1 * torch.randn(shape, generator=g, device=device)
+        else:
+            t = 0.02 * torch.randn(shape, generator=g, device=device)
+        sd[name] = t.to(torch.bfloat16)
+    return sd
+
+
+def run_vr2(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    import video_r2_b200 as vr2
+    from video_r2_b200.shard import all_gather_ragged, partition_slices
+
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = vr2.VisionConfig()
+    tower = vr2.VisionTower(cfg, synth_state_dict(cfg, dev), device=dev)
+
+    grid = [list(CLIP)] * world
+    shares = partition_slices(grid, world)
+    me = shares[rank]
+    my_grid = [list(r) for r in me.grid]
+    n_local = me.patch_hi - me.patch_lo
+    tok_local = me.token_hi - me.token_lo
+    counts = [s.token_hi - s.token_lo for s in shares]
+    tokens_total = sum(counts)
+    n_rot = 4  # 4 x 38.5 MB of pixels > 126 MB L2; weights (1.35 GB) + activations (0.44 GB) stream every step anyway
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    pix_dev = [torch.randn(n_local, cfg.patch_dim, generator=g, device=dev).to(torch.bfloat16) for _ in range(n_rot)]
+    pix_host = [p.cpu().pin_memory() for p in pix_dev]
+    # batch of `world` rows: text, <vision_start>, video pads, <vision_end>, text
+    per_clip = CLIP[0] * CLIP[1] * CLIP[2] // 4
+    row = [1000 + i for i in range(TEXT_BEFORE)] + [151652] + [151656] * per_clip + [151653] + [2000 + i for i in range(TEXT_AFTER)]
+    ids_host = torch.tensor([row] * world, dtype=torch.int64).pin_memory()
+    ids_dev = ids_host.to(dev)
+    vid_thw = torch.tensor(grid, dtype=torch.int64, device=dev)
+    spg = torch.tensor([2.0 / 0.7] * world, dtype=torch.float32, device=dev)
+    out_host = torch.empty((tok_local, cfg.out_hidden_size), dtype=torch.bfloat16).pin_memory()
+    pos_host = torch.empty((3, world, len(row)), dtype=torch.int64).pin_memory()
+
+    def step_device(i):
+        local = tower(pix_dev[i % n_rot], my_grid)
+        full = all_gather_ragged(local, counts) if world > 1 else local
+        pos, delta = vr2.get_rope_index(ids_dev, None, vid_thw, spg, None)
+        return local, full, pos
+
+    def step_e2e(i):
+        x = pix_host[i % n_rot].to(dev, non_blocking=True)
+        ids = ids_host.to(dev, non_blocking=True)
+        local = tower(x, my_grid)
+        full = all_gather_ragged(local, counts) if world > 1 else local
+        pos, delta = vr2.get_rope_index(ids, None, vid_thw, spg, None)
+        out_host.copy_(local, non_blocking=True)
+        pos_host.copy_(pos, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller consumes the result
+        return full
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    for i in range(max(3, args.warmup)):
+        step_device(i)
+    # ---- value: inputs resident in HBM; the dominant kernel is timed live with CUDA events
+    tower.profile(["gate_up"])
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_total = timed(step_device, args.steps)
+    clocks = sampler.stop()
+    prof = tower.profile_read()
+    tower.profile(())
+    ms_step = ms_total / args.steps
+    value = tokens_total / (ms_step * 1e-3)
+    # ---- e2e: host buffers in, host buffers out
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps) / args.steps
+    e2e_value = tokens_total / (ms_e2e * 1e-3)
+    h2d = pix_host[0].numel() * 2 + ids_host.numel() * 8
+    d2h = out_host.numel() * 2 + pos_host.numel() * 8
+    # ---- per-kind breakdown (untimed pass, all kinds) for the profile notes
+    tower.profile(tower.KERNEL_KINDS)
+    for i in range(3):
+        step_device(i)
+    breakdown = tower.profile_read()
+    tower.profile(())
+
+    peaks, peak_src = _peaks()
+    gu_ms, gu_n = prof.get("gate_up", (0.0, 0))
+    gu_avg = gu_ms / max(1, gu_n)
+    gu_flops = 2.0 * n_local * (2 * cfg.intermediate_size) * cfg.hidden_size  # algorithmic (unpadded) per launch
+    achieved = gu_flops / (gu_avg * 1e-3) / 1e12 if gu_avg > 0 else None
+    peak = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_top_kernel.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    launches = tower.launch_count(my_grid) + 2
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {
+            "workload": f"Video-R2 eval setting x{world}: {world} clip(s) of 32 frames 448x448 (grid_thw [16,32,32] each, "
+                        f"{tokens_total} visual tokens), Qwen2.5-VL-7B vision tower random init + get_rope_index; "
+                        "slices sharded over ranks, one all-gather of embeddings",
+            "frames_per_sec": value / per_clip * 2 * CLIP[0],
+            "l2": "pixel inputs rotate over 4 buffers (154 MB > 126 MB L2); 1.35 GB of weights and 0.44 GB of "
+                  "activations stream through HBM every step",
+            "operands": "bf16 GEMM/attention operands, fp32 accumulate, fp32 residual stream",
+            "step_tflops": tokens_total * FLOP_PER_TOKEN / (ms_step * 1e-3) / 1e12 / world,
+        },
+        "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                     "kernel": "gate|up GEMM + SwiGLU epilogue (42.6% of FLOPs)", "launches_timed": gu_n,
+                     "avg_launch_ms": gu_avg, "peak_source": peak_src + ", sustained bf16"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e},
+        "gpu_launches": launches * args.steps,
+        "clocks": clocks,
+        "breakdown_ms_per_step": {k: round(v[0] / 3, 4) for k, v in breakdown.items()},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            kind, run = cpu_reference_runner()
+            run(1)
+            slices = 2
+            dt = run(slices)
+            tok = slices * CLIP[1] * CLIP[2] // 4
+            line["cpu_baseline"] = {"value": tok / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+                                    "sample": f"{slices} of the {CLIP[0]} temporal slices of the same clip ({tok} tokens), "
+                                              f"one forward after one warm-up, fp32 sdpa, {dt:.1f} s"}
+        except Exception as e:
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"failed: {e!r}"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="vr2", choices=["vr2", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus:
+        if args.gpus > 1 and world == 1:
+            # convenience: relaunch under torchrun
+            import subprocess
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+                   "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.abspath(__file__)] + sys.argv[1:]
+            sys.exit(subprocess.call(cmd))
+        args.gpus = world
+    run_vr2(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -135,6 +135,26 @@ size_t vr2_tower_workspace_bytes(const vr2_tower* tower, int64_t n_patches);
  * vr2_tower_workspace_bytes() bytes, 1024-byte aligned. */
 int vr2_tower_forward(vr2_tower* tower, const vr2_plan* plan, const void* pixels_dev, int32_t pixels_dtype,
                       void* out_dev, int32_t out_dtype, void* workspace_dev, size_t workspace_bytes, void* stream);
+/* Per-kernel-kind device timing.  vr2_tower_profile(mask) selects kinds (bit k = vr2_kernel_kind k; 0 turns it
+ * off) and resets the counters; while selected, vr2_tower_forward brackets every launch of that kind with a
+ * cudaEvent pair on the caller's stream.  vr2_tower_profile_read synchronises on those events and returns the
+ * summed milliseconds and launch counts per kind (arrays of VR2_K_COUNT), then resets. */
+typedef enum vr2_kernel_kind {
+  VR2_K_CAST = 0,
+  VR2_K_PATCH_EMBED = 1,
+  VR2_K_QKV = 2,
+  VR2_K_ATTN_WINDOW = 3,
+  VR2_K_ATTN_FULL = 4,
+  VR2_K_PROJ = 5,
+  VR2_K_GATE_UP = 6,
+  VR2_K_DOWN = 7,
+  VR2_K_MERGER_NORM = 8,
+  VR2_K_FC1 = 9,
+  VR2_K_FC2 = 10,
+  VR2_K_COUNT = 11
+} vr2_kernel_kind;
+int vr2_tower_profile(vr2_tower* tower, uint32_t kind_mask);
+int vr2_tower_profile_read(vr2_tower* tower, double* ms_by_kind, int64_t* launches_by_kind);
 /* Number of kernels vr2_tower_forward enqueues for this plan (for gpu_launches). */
 int64_t vr2_tower_launch_count(const vr2_tower* tower, const vr2_plan* plan, int32_t pixels_dtype);
 

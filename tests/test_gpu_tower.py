@@ -50,7 +50,8 @@ def test_tower_vs_hf_golden(path):
     print(f"\n{os.path.basename(path)}: fp32-out max-abs {e32:.4f} cos {c32:.6f} min-row-cos {r32:.6f} | "
           f"bf16-out max-abs {e16:.4f} cos {c16:.6f}")
     assert c16 >= 0.9995 and r16 >= 0.9995
-    bound = 2e-2 if cfg.depth <= 4 else 8e-2  # depth 32: bf16-operand floor measured in SURVEY §7.3 (0.06)
+    # bf16-operand floor measured in SURVEY §7.3: merger alone 0.0205, whole depth-32 tower 0.06
+    bound = 3e-2 if cfg.depth <= 4 else 8e-2
     assert e32 <= bound, (e32, bound)
 
 
@@ -67,7 +68,7 @@ def test_tower_vs_oracle_multi_clip_and_dummy():
         out = tower(x.cuda(), grid, out_dtype=torch.float32)
         e, c, r = _stats(out, ref)
         print(f"\n{grid}: max-abs {e:.4f} cos {c:.6f}")
-        assert e <= 2e-2 and c >= 0.9995, (grid, e, c)
+        assert e <= 3e-2 and c >= 0.9995, (grid, e, c)
     # fp32 pixels in -> fp32 out (the oracle's own dtype), identical numbers to the bf16 path for bf16-exact pixels
     grid = [[2, 10, 14]]
     x = torch.randn(280, 1176, generator=torch.Generator().manual_seed(10)).to(torch.bfloat16)

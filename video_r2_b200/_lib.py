@@ -75,6 +75,8 @@ SIGNATURES = {
     "vr2_tower_finalize": (C.c_int, [_P]),
     "vr2_tower_workspace_bytes": (C.c_size_t, [_P, C.c_int64]),
     "vr2_tower_forward": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int32, _P, C.c_size_t, _P]),
+    "vr2_tower_profile": (C.c_int, [_P, C.c_uint32]),
+    "vr2_tower_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "vr2_tower_launch_count": (C.c_int64, [_P, _P, C.c_int32]),
     "vr2_rope_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "vr2_rope_index": (C.c_int, [C.POINTER(RopeConfig), _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, _P,

@@ -66,6 +66,11 @@ struct vr2_tower {
   vr2::Tensor fc1_w, fc1_b;        // bf16 [md, md], fp32 [md]
   vr2::Tensor fc2_w, fc2_b;        // bf16 [out, md], fp32 [out]
   std::vector<void*> allocs;
+  // optional per-kind CUDA-event timing (vr2_tower_profile)
+  uint32_t prof_mask = 0;
+  std::vector<cudaEvent_t> prof_events;  // pairs (begin, end)
+  std::vector<int> prof_kind;            // kind of pair i
+  size_t prof_used = 0;                  // pairs recorded since the last reset
 };
 
 using namespace vr2;
@@ -86,6 +91,33 @@ bool is_full_layer(const vr2_tower* t, int l) {
     if (t->cfg.fullatt_block_indexes[i] == l) return true;
   return false;
 }
+
+constexpr size_t kMaxProfPairs = 8192;
+
+// Records an event pair around the launches issued while it is alive, when `kind` is selected.
+struct ProfScope {
+  vr2_tower* t;
+  cudaStream_t s;
+  cudaEvent_t end = nullptr;
+  ProfScope(vr2_tower* tower, int kind, cudaStream_t stream) : t(tower), s(stream) {
+    if (!(t->prof_mask & (1u << kind)) || t->prof_used >= kMaxProfPairs) return;
+    const size_t i = t->prof_used;
+    if (t->prof_events.size() < 2 * (i + 1)) {
+      cudaEvent_t a, b;
+      if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) return;
+      t->prof_events.push_back(a);
+      t->prof_events.push_back(b);
+      t->prof_kind.push_back(kind);
+    }
+    t->prof_kind[i] = kind;
+    cudaEventRecord(t->prof_events[2 * i], s);
+    end = t->prof_events[2 * i + 1];
+    t->prof_used = i + 1;
+  }
+  ~ProfScope() {
+    if (end != nullptr) cudaEventRecord(end, s);
+  }
+};
 
 }  // namespace
 
@@ -157,6 +189,7 @@ extern "C" int vr2_tower_create(const vr2_tower_config* cfg, int32_t device, vr2
 extern "C" void vr2_tower_destroy(vr2_tower* t) {
   if (t == nullptr) return;
   for (void* p : t->allocs) cudaFree(p);
+  for (cudaEvent_t e : t->prof_events) cudaEventDestroy(e);
   delete t;
 }
 
@@ -316,7 +349,8 @@ extern "C" int vr2_tower_forward(vr2_tower* t, const vr2_plan* plan, const void*
   const int parts = h / 256;
   const float eps = t->cfg.rms_norm_eps;
   const char* msg = "";
-  auto G = [&](const GemmArgs& a, const char* what) -> int {
+  auto G = [&](const GemmArgs& a, int kind, const char* what) -> int {
+    ProfScope prof(t, kind, s);
     cudaError_t e = gemm_launch(a, t->num_sms, s, &msg);
     if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? VR2_ERR_ARG : VR2_ERR_CUDA, "vr2_tower_forward: %s: %s %s", what, cudaGetErrorString(e), msg);
     return VR2_OK;
@@ -326,6 +360,7 @@ extern "C" int vr2_tower_forward(vr2_tower* t, const vr2_plan* plan, const void*
   // ---- patch embed (Conv3d with kernel == stride == a [N,1176] x [1176,1280] GEMM), stored window-permuted
   const __nv_bfloat16* pix = static_cast<const __nv_bfloat16*>(pixels);
   if (pixels_dtype == VR2_F32) {
+    ProfScope prof(t, VR2_K_CAST, s);
     VR2_CUDA(cast_f32_to_bf16(static_cast<const float*>(pixels), w.pix, N * t->patch_k, s));
     pix = w.pix;
   }
@@ -338,7 +373,7 @@ extern "C" int vr2_tower_forward(vr2_tower* t, const vr2_plan* plan, const void*
     a.row_map = plan->row_map;
     a.norm_w = static_cast<const float*>(t->layers[0].norm1_w.ptr);
     a.ssq = w.ssq;
-    if ((rc = G(a, "patch_embed")) != VR2_OK) return rc;
+    if ((rc = G(a, VR2_K_PATCH_EMBED, "patch_embed")) != VR2_OK) return rc;
   }
 
   for (int l = 0; l < t->cfg.depth; ++l) {
@@ -352,10 +387,11 @@ extern "C" int vr2_tower_forward(vr2_tower* t, const vr2_plan* plan, const void*
       a.out_bf16 = w.qkv; a.ld_out = 3 * h;
       a.ssq_in = w.ssq; a.ssq_parts = parts; a.inv_dim = 1.0f / h; a.eps = eps;
       a.cos_tab = plan->cos_tab; a.sin_tab = plan->sin_tab;
-      if ((rc = G(a, "qkv")) != VR2_OK) return rc;
+      if ((rc = G(a, VR2_K_QKV, "qkv")) != VR2_OK) return rc;
     }
     {
       const bool full = is_full_layer(t, l);
+      ProfScope prof(t, full ? VR2_K_ATTN_FULL : VR2_K_ATTN_WINDOW, s);
       VR2_CUDA(attention_launch(w.qkv, w.att, full ? plan->tiles_full : plan->tiles_window,
                                 static_cast<int>(full ? plan->n_tiles_full : plan->n_tiles_window), t->cfg.num_heads,
                                 3 * h, h, s));
@@ -369,7 +405,7 @@ extern "C" int vr2_tower_forward(vr2_tower* t, const vr2_plan* plan, const void*
       a.x = w.x; a.ldx = h; a.out_bf16 = w.xb; a.ld_out = h;
       a.norm_w = static_cast<const float*>(L.norm2_w.ptr);
       a.ssq = w.ssq;
-      if ((rc = G(a, "proj")) != VR2_OK) return rc;
+      if ((rc = G(a, VR2_K_PROJ, "proj")) != VR2_OK) return rc;
     }
     {
       GemmArgs a{};
@@ -379,7 +415,7 @@ extern "C" int vr2_tower_forward(vr2_tower* t, const vr2_plan* plan, const void*
       a.bias = static_cast<const float*>(L.gu_b.ptr);
       a.out_bf16 = w.hbuf; a.ld_out = t->ipad;
       a.ssq_in = w.ssq; a.ssq_parts = parts; a.inv_dim = 1.0f / h; a.eps = eps;
-      if ((rc = G(a, "gate_up")) != VR2_OK) return rc;
+      if ((rc = G(a, VR2_K_GATE_UP, "gate_up")) != VR2_OK) return rc;
     }
     {
       GemmArgs a{};
@@ -390,14 +426,17 @@ extern "C" int vr2_tower_forward(vr2_tower* t, const vr2_plan* plan, const void*
       a.x = w.x; a.ldx = h; a.out_bf16 = w.xb; a.ld_out = h;
       a.norm_w = static_cast<const float*>(l + 1 < t->cfg.depth ? t->layers[l + 1].norm1_w.ptr : t->lnq_w.ptr);
       a.ssq = w.ssq;
-      if ((rc = G(a, "down")) != VR2_OK) return rc;
+      if ((rc = G(a, VR2_K_DOWN, "down")) != VR2_OK) return rc;
     }
   }
 
   // ---- PatchMerger: ln_q per patch row, then 4 consecutive window-order rows form one merged token
   const int64_t T = plan->n_tokens;
   const int md = t->merge_dim;
-  VR2_CUDA(rmsnorm_to_bf16(w.x, static_cast<const float*>(t->lnq_w.ptr), w.qkv, N, h, eps, s));
+  {
+    ProfScope prof(t, VR2_K_MERGER_NORM, s);
+    VR2_CUDA(rmsnorm_to_bf16(w.x, static_cast<const float*>(t->lnq_w.ptr), w.qkv, N, h, eps, s));
+  }
   {
     GemmArgs a{};
     a.A = w.qkv; a.lda = md; a.W = static_cast<const __nv_bfloat16*>(t->fc1_w.ptr); a.ldw = md;
@@ -405,7 +444,7 @@ extern "C" int vr2_tower_forward(vr2_tower* t, const vr2_plan* plan, const void*
     a.epilogue = EPI_STORE; a.flags = GEMM_GELU;
     a.bias = static_cast<const float*>(t->fc1_b.ptr);
     a.out_bf16 = w.hbuf; a.ld_out = md;
-    if ((rc = G(a, "merger.fc1")) != VR2_OK) return rc;
+    if ((rc = G(a, VR2_K_FC1, "merger.fc1")) != VR2_OK) return rc;
   }
   {
     GemmArgs a{};
@@ -416,8 +455,30 @@ extern "C" int vr2_tower_forward(vr2_tower* t, const vr2_plan* plan, const void*
     a.out_bf16 = static_cast<__nv_bfloat16*>(out); a.out_f32 = static_cast<float*>(out);
     a.ld_out = t->cfg.out_hidden_size;
     a.row_map = plan->out_map;  // inverse window permute fused into the store (HF :512-513)
-    if ((rc = G(a, "merger.fc2")) != VR2_OK) return rc;
+    if ((rc = G(a, VR2_K_FC2, "merger.fc2")) != VR2_OK) return rc;
   }
+  return VR2_OK;
+}
+
+extern "C" int vr2_tower_profile(vr2_tower* t, uint32_t kind_mask) {
+  if (t == nullptr) return fail(VR2_ERR_ARG, "vr2_tower_profile: null tower");
+  t->prof_mask = kind_mask;
+  t->prof_used = 0;
+  return VR2_OK;
+}
+
+extern "C" int vr2_tower_profile_read(vr2_tower* t, double* ms_by_kind, int64_t* launches_by_kind) {
+  if (t == nullptr || ms_by_kind == nullptr || launches_by_kind == nullptr)
+    return fail(VR2_ERR_ARG, "vr2_tower_profile_read: null argument");
+  for (int k = 0; k < VR2_K_COUNT; ++k) { ms_by_kind[k] = 0.0; launches_by_kind[k] = 0; }
+  for (size_t i = 0; i < t->prof_used; ++i) {
+    VR2_CUDA(cudaEventSynchronize(t->prof_events[2 * i + 1]));
+    float ms = 0.f;
+    VR2_CUDA(cudaEventElapsedTime(&ms, t->prof_events[2 * i], t->prof_events[2 * i + 1]));
+    ms_by_kind[t->prof_kind[i]] += ms;
+    launches_by_kind[t->prof_kind[i]] += 1;
+  }
+  t->prof_used = 0;
   return VR2_OK;
 }
 

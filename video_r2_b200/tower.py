@@ -255,5 +255,23 @@ class VisionTower:
 
     __call__ = forward
 
+    KERNEL_KINDS = ("cast", "patch_embed", "qkv", "attn_window", "attn_full", "proj", "gate_up", "down",
+                    "merger_norm", "fc1", "fc2")
+
+    def profile(self, kinds=()):
+        """Select kernel kinds to time with CUDA events inside forward (() turns profiling off)."""
+        mask = 0
+        for k in kinds:
+            mask |= 1 << self.KERNEL_KINDS.index(k)
+        check(lib().vr2_tower_profile(self._h, mask), "vr2_tower_profile")
+
+    def profile_read(self):
+        """-> {kind: (milliseconds, launches)} accumulated since the last read (synchronises)."""
+        n = len(self.KERNEL_KINDS)
+        ms = (C.c_double * 16)()
+        cnt = (C.c_int64 * 16)()
+        check(lib().vr2_tower_profile_read(self._h, ms, cnt), "vr2_tower_profile_read")
+        return {self.KERNEL_KINDS[i]: (ms[i], cnt[i]) for i in range(n) if cnt[i]}
+
     def launch_count(self, grid_thw, dtype=torch.bfloat16) -> int:
         return int(lib().vr2_tower_launch_count(self._h, self.plan(grid_thw)._h, _dtype_code(dtype)))
