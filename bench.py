@@ -52,7 +52,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.sm, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.ok = False
         try:
             import pynvml
@@ -75,7 +75,7 @@ class ClockSampler(threading.Thread):
             getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
             getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
         }
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 try:
@@ -87,10 +87,10 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(self.period)
+            self._halt.wait(self.period)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(self.reasons), "samples": len(self.sm)}

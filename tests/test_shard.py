@@ -1,0 +1,79 @@
+"""CPU: host logic of the multi-GPU path — slice partition and the ragged all-gather — with a
+world_size-2 (and 3) gloo group.  The tower itself is replaced by a deterministic row function, so
+this checks routing (who encodes what, where it lands), not arithmetic."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from video_r2_b200 import shard
+
+CFG5 = [(16, 448, 448), (32, 448, 448), (64, 448, 448), (128, 336, 588), (8, 280, 504), (32, 280, 504),
+        (128, 280, 504), (16, 336, 588), (64, 336, 588), (4, 448, 448), (32, 392, 392), (64, 224, 392),
+        (16, 504, 280), (128, 224, 224), (2, 392, 392), (48, 364, 644)]
+
+
+def grid_of(frames, H, W):
+    return [frames // 2, H // 14, W // 14]
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_partition_covers_everything_once_and_balances(world):
+    grid = [grid_of(*c) for c in CFG5]  # BASELINE config 5: ragged mixed-resolution batch
+    shares = shard.partition_slices(grid, world)
+    assert len(shares) == world
+    n_patches = sum(t * h * w for t, h, w in grid)
+    assert shares[0].patch_lo == 0 and shares[-1].patch_hi == n_patches
+    for a, b in zip(shares, shares[1:]):
+        assert a.patch_hi == b.patch_lo and a.token_hi == b.token_lo
+    for s in shares:
+        assert sum(t * h * w for t, h, w in s.grid) == s.patch_hi - s.patch_lo
+        assert (s.patch_hi - s.patch_lo) == 4 * (s.token_hi - s.token_lo)
+    # concatenated local grids reproduce the slice sequence of the global grid
+    flat = [(h, w) for t, h, w in grid for _ in range(t)]
+    got = [(h, w) for s in shares for t, h, w in s.grid for _ in range(t)]
+    assert flat == got
+    costs = [s.cost for s in shares]
+    assert max(costs) <= 1.08 * (sum(costs) / world)  # frame-balanced within a slice
+
+
+def test_partition_fewer_slices_than_ranks():
+    shares = shard.partition_slices([[3, 8, 8]], 8)
+    assert sum(s.token_hi - s.token_lo for s in shares) == 3 * 16
+    assert sum(1 for s in shares if s.patch_hi > s.patch_lo) == 3
+
+
+class FakeTower:
+    """Row function standing in for the tower: token i of a call = mean of its 4 patch rows' first 8 features."""
+
+    def __init__(self):
+        self.cfg = type("C", (), {"spatial_merge_size": 2, "out_hidden_size": 8})()
+        self.device = torch.device("cpu")
+
+    def __call__(self, pixels, grid, out_dtype=None):
+        assert pixels.shape[0] == sum(t * h * w for t, h, w in grid)
+        return pixels[:, :8].reshape(-1, 4, 8).mean(1)
+
+
+def _worker(rank, world, port, grid, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        n = sum(t * h * w for t, h, w in grid)
+        pixels = torch.arange(n * 16, dtype=torch.float32).reshape(n, 16)
+        out = shard.encode_sharded(FakeTower(), pixels, grid)
+        ref = FakeTower()(pixels, grid)
+        ret[rank] = bool(torch.equal(out, ref))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,grid", [(2, [[4, 8, 8]]), (2, [[3, 8, 12], [2, 4, 4], [5, 6, 8]]), (3, [[2, 4, 4]])])
+def test_encode_sharded_gloo(world, grid):
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    port = 29600 + world * 7 + len(grid)
+    mp.spawn(_worker, args=(world, port, grid, ret), nprocs=world, join=True)
+    assert all(ret[r] for r in range(world)), dict(ret)

@@ -11,7 +11,7 @@ from .rope_index import RopeConfig, get_rope_index
 from .tower import Plan, VisionConfig, VisionTower, gather_rows
 
 __all__ = ["LIB_PATH", "Vr2Error", "lib", "RopeConfig", "get_rope_index", "Plan", "VisionConfig", "VisionTower",
-           "gather_rows", "install", "uninstall"]
+           "gather_rows", "install", "uninstall", "refresh"]
 
 
 def install(*args, **kwargs):
@@ -22,3 +22,8 @@ def install(*args, **kwargs):
 def uninstall(*args, **kwargs):
     from .patch import uninstall as _uninstall
     return _uninstall(*args, **kwargs)
+
+
+def refresh(module):
+    from .patch import refresh as _refresh
+    return _refresh(module)
