@@ -4,12 +4,16 @@
 //
 // One CTA per SM loops over 128 x BN output tiles (tile id -> n fastest, so the
 // 148 resident CTAs share a band of A rows and all of W through L2).  Roles:
-//   warp 4 (one lane)  TMA producer: 128B-swizzled A/W k-blocks into a 4-stage ring
-//   warp 5 (one lane)  tcgen05.mma issuer: 4 x (128 x BN x 16) per k-block, two
-//                      accumulator stages in TMEM (2 x 256 columns)
-//   warps 0-3          epilogue: tcgen05.ld of the finished accumulator (thread =
-//                      row), fused bias / residual / RMS scale / rotary / SwiGLU /
-//                      GELU, stores; overlaps the next tile's MMAs
+//   TMA producer: 128B-swizzled A/W k-blocks into a 4-stage ring
+//   tcgen05.mma issuer: 4 x (128 x BN x 16) per k-block, two accumulator stages in
+//                      TMEM (2 x 256 columns)
+//   warps 0..4G-1      epilogue: G column groups x 4 lane quarters (a warp may only
+//                      read TMEM lanes 32*(warp%4)..+31); tcgen05.ld of the finished
+//                      accumulator (thread = row), fused bias / residual / RMS
+//                      scale / rotary / SwiGLU / GELU, stores; overlaps the next
+//                      tile's MMAs.  G=4 (16 warps) for BN=256, G=3 (one head each)
+//                      for the QKV tile of 240 columns
+//   warp 4G (one lane)   TMA producer,  warp 4G+1 (one lane)  tcgen05.mma issuer
 // Replaces the cuBLAS/cuDNN calls behind nn.Linear / nn.Conv3d in
 // HF modeling_qwen2_5_vl.py:108-114 (patch embed), :221-287 (qkv, proj),
 // :87-88 (gate/up/down), :144-146 (merger).
@@ -29,27 +33,95 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 64;   // one 128-byte swizzle atom of bf16
 constexpr int UK = 16;   // K per tcgen05.mma (bf16)
-constexpr int kThreads = 192;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
 
 template <int BN>
 struct Cfg {
+  static constexpr int groups = BN == 240 ? 3 : 4;        // epilogue column groups
+  static constexpr int epi_warps = 4 * groups;
+  static constexpr int threads = (epi_warps + 2) * 32;
+  static constexpr int group_cols = BN / groups;           // 64 (BN=256) or 80 (BN=240)
   static constexpr int a_bytes = BM * BK * 2;
   static constexpr int b_bytes = BN * BK * 2;
   static constexpr int stage_bytes = a_bytes + b_bytes;
   static constexpr int stages = (196 * 1024) / stage_bytes;
   static constexpr int bar_bytes = 256;
-  static constexpr int smem_bytes = stages * stage_bytes + bar_bytes + 1024;  // +1024: manual alignment
+  static constexpr int staging_bytes = epi_warps * 2048;   // per-warp epilogue staging
+  static constexpr int smem_bytes = stages * stage_bytes + bar_bytes + staging_bytes + 1024;  // +1024: manual alignment
+  static_assert(smem_bytes <= 232448, "exceeds the 227 KB shared-memory limit");
   static_assert(stage_bytes % 1024 == 0, "stage must keep 1024-byte alignment for SWIZZLE_128B");
   static_assert(stages >= 3, "pipeline too shallow");
 };
 
+constexpr int kStageBytes = 2048;  // per epilogue warp
+
+// Per-warp staging tile that turns thread-per-row register data into row-contiguous global
+// accesses.  Two views of the same 2 KB: fp32 [32 rows][16] (64-byte rows, 4 x 16-byte chunks,
+// chunk index XOR-swizzled by (row >> 1) & 3 so both the row-per-thread and the 8-rows-per-
+// instruction patterns are bank-conflict free) and bf16 [32 rows][16] (32-byte rows).
+struct Stage {
+  uint8_t* base;
+  __device__ __forceinline__ float4* f4(int row, int chunk) const {
+    return reinterpret_cast<float4*>(base + row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4));
+  }
+  __device__ __forceinline__ uint4* h8(int row, int half) const {
+    return reinterpret_cast<uint4*>(base + row * 32 + (half << 4));
+  }
+  // global [32 x 16 fp32] piece (row pitch ld elements) -> staging; lanes cover 8 rows x 64 B per pass
+  __device__ __forceinline__ void load_f32(const float* g, int64_t ld, int rows_valid, int lane) const {
+    const int chunk = lane & 3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int row = (lane >> 2) + 8 * k;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < rows_valid) v = *reinterpret_cast<const float4*>(g + row * ld + chunk * 4);
+      *f4(row, chunk) = v;
+    }
+  }
+  // same, for a piece only `width` (8 or 16) columns wide
+  __device__ __forceinline__ void load_f32_w(const float* g, int64_t ld, int rows_valid, int lane, int width) const {
+    const int chunk = lane & 3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int row = (lane >> 2) + 8 * k;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < rows_valid && chunk * 4 < width) v = __ldg(reinterpret_cast<const float4*>(g + row * ld + chunk * 4));
+      *f4(row, chunk) = v;
+    }
+  }
+  __device__ __forceinline__ void store_f32(float* g, int64_t ld, int rows_valid, int lane) const {
+    const int chunk = lane & 3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int row = (lane >> 2) + 8 * k;
+      if (row < rows_valid) *reinterpret_cast<float4*>(g + row * ld + chunk * 4) = *f4(row, chunk);
+    }
+  }
+  // staging bf16 [32 x 16] -> global; lanes cover 16 rows x 32 B per pass
+  __device__ __forceinline__ void store_bf16(__nv_bfloat16* g, int64_t ld, int rows_valid, int lane) const {
+    const int half = lane & 1;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int row = (lane >> 1) + 16 * k;
+      if (row < rows_valid) *reinterpret_cast<uint4*>(g + row * ld + half * 8) = *h8(row, half);
+    }
+  }
+  __device__ __forceinline__ void store_bf16_w(__nv_bfloat16* g, int64_t ld, int rows_valid, int lane, int width) const {
+    const int half = lane & 1;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int row = (lane >> 1) + 16 * k;
+      if (row < rows_valid && half * 8 < width) *reinterpret_cast<uint4*>(g + row * ld + half * 8) = *h8(row, half);
+    }
+  }
+};
+
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
-__device__ __forceinline__ float silu(float v) { return v / (1.0f + __expf(-v)); }
+__device__ __forceinline__ float silu(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(Cfg<BN>::threads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -62,6 +134,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* acc_full = empty_bar + C::stages;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint8_t* stage_base = smem + C::stages * C::stage_bytes + C::bar_bytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -70,7 +143,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int num_tiles = num_m_blocks * num_n_blocks;
   const int num_k_blocks = (p.K + BK - 1) / BK;
 
-  if (warp == 4 && lane == 0) {
+  constexpr int kProducerWarp = C::epi_warps;
+  constexpr int kMmaWarp = C::epi_warps + 1;
+  if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < C::stages; ++s) {
@@ -79,11 +154,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4);  // one arrive per epilogue warp
+      mbar_init(&acc_empty[s], C::epi_warps);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
-  if (warp == 5) {
+  if (warp == kMmaWarp) {
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
@@ -92,7 +167,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == kProducerWarp) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t it = 0;
@@ -111,7 +186,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
@@ -142,7 +217,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 0-3)
+    // ------------------------------------------------------------ epilogue (warps 0 .. 4G-1)
+    // thread = accumulator row.  A row-per-thread global access touches 32 cache lines per
+    // instruction (half-written sectors); every piece therefore goes through this warp's 2 KB
+    // staging buffer so that global loads/stores are row-contiguous (ncu r01b: 32 sectors/request,
+    // L1 64 %, tensor pipe 24-54 % before; see profiles/).
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may read
+    const int cg = warp >> 2;              // column group
+    constexpr int GC = C::group_cols;
+    const Stage st{stage_base + warp * kStageBytes};
     uint32_t local = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
       const int n_blk = tile % num_n_blocks;
@@ -152,163 +235,249 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const uint32_t use = local >> 1;
       mbar_wait(&acc_full[as], use & 1u);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + as * kAccStride;
-      const int r = m0 + warp * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * kAccStride;
+      const int row0 = m0 + quarter * 32;    // first row of this warp
+      const int r = row0 + lane;
       const bool valid = r < p.M;
+      const int rows_valid = min(32, max(0, p.M - row0));
 
       if constexpr (EPI == EPI_STORE) {
-        const int64_t dest = valid ? (p.row_map ? p.row_map[r] : r) : 0;
+        const bool direct = p.row_map != nullptr;   // scattered rows (inverse window permute): row-per-thread stores
+        const int64_t dest = valid ? (direct ? p.row_map[r] : r) : 0;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(taddr + c, v);
+        for (int c = cg * GC; c < (cg + 1) * GC; c += 16) {
+          if (n0 + c >= p.N) break;        // N % 32 == 0 is checked on the host
+          uint32_t v[16];
+          tmem_ld16(taddr + c, v);
           tmem_ld_wait();
-          if (valid) {
-            float f[32];
+          float f[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int col = n0 + c + j;
-              float t = __uint_as_float(v[j]);
-              if (p.bias != nullptr && col < p.N) t += __ldg(p.bias + col);
-              if (p.flags & GEMM_GELU) t = gelu_erf(t);
-              f[j] = t;
-            }
-            if (p.flags & GEMM_OUT_F32) {
-              float* o = p.out_f32 + dest * p.ld_out + n0 + c;
+          for (int j = 0; j < 16; j += 4) {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + j));
+            f[j] = __uint_as_float(v[j]) + b.x;
+            f[j + 1] = __uint_as_float(v[j + 1]) + b.y;
+            f[j + 2] = __uint_as_float(v[j + 2]) + b.z;
+            f[j + 3] = __uint_as_float(v[j + 3]) + b.w;
+          }
+          if (p.flags & GEMM_GELU) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                if (n0 + c + j < p.N) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+            for (int j = 0; j < 16; ++j) f[j] = gelu_erf(f[j]);
+          }
+          if (p.flags & GEMM_OUT_F32) {
+            if (direct) {
+              if (valid) {
+                float* o = p.out_f32 + dest * p.ld_out + n0 + c;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                  *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              }
             } else {
-              __nv_bfloat16* o = p.out_bf16 + dest * p.ld_out + n0 + c;
 #pragma unroll
-              for (int j = 0; j < 32; j += 8)
-                if (n0 + c + j < p.N)
-                  *reinterpret_cast<uint4*>(o + j) =
-                      make_uint4(pack_bf16x2(f[j], f[j + 1]), pack_bf16x2(f[j + 2], f[j + 3]),
-                                 pack_bf16x2(f[j + 4], f[j + 5]), pack_bf16x2(f[j + 6], f[j + 7]));
+              for (int j = 0; j < 4; ++j) *st.f4(lane, j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+              __syncwarp();
+              st.store_f32(p.out_f32 + static_cast<int64_t>(row0) * p.ld_out + n0 + c, p.ld_out, rows_valid, lane);
+              __syncwarp();
+            }
+          } else {
+            const uint4 p0 = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+            const uint4 p1 = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+            if (direct) {
+              if (valid) {
+                __nv_bfloat16* o = p.out_bf16 + dest * p.ld_out + n0 + c;
+                *reinterpret_cast<uint4*>(o) = p0;
+                *reinterpret_cast<uint4*>(o + 8) = p1;
+              }
+            } else {
+              *st.h8(lane, 0) = p0;
+              *st.h8(lane, 1) = p1;
+              __syncwarp();
+              st.store_bf16(p.out_bf16 + static_cast<int64_t>(row0) * p.ld_out + n0 + c, p.ld_out, rows_valid, lane);
+              __syncwarp();
             }
           }
         }
       } else if constexpr (EPI == EPI_RESID) {
-        const int64_t dest = valid ? (p.row_map ? p.row_map[r] : r) : 0;
+        const bool direct = p.row_map != nullptr;   // patch embed: rows scatter through the window permute
+        const int64_t dest = valid ? (direct ? p.row_map[r] : r) : 0;
         float ss = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          uint32_t v[32];
-          tmem_ld32(taddr + c, v);
+        for (int c = cg * GC; c < (cg + 1) * GC; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c, v);
+          float* xg = p.x + static_cast<int64_t>(row0) * p.ldx + n0 + c;          // piece origin (identity rows)
+          if (!direct && (p.flags & GEMM_ADD_RESID)) st.load_f32(xg, p.ldx, rows_valid, lane);
           tmem_ld_wait();
-          if (valid) {
-            float* xr = p.x + dest * p.ldx + n0 + c;
-            __nv_bfloat16* xb = p.out_bf16 + dest * p.ld_out + n0 + c;
+          __syncwarp();
+          float f[16];
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              float f[8];
-#pragma unroll
-              for (int q = 0; q < 8; ++q) f[q] = __uint_as_float(v[j + q]);
-              if (p.bias != nullptr) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + j));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + j + 4));
-                f[0] += b0.x; f[1] += b0.y; f[2] += b0.z; f[3] += b0.w;
-                f[4] += b1.x; f[5] += b1.y; f[6] += b1.z; f[7] += b1.w;
-              }
-              if (p.flags & GEMM_ADD_RESID) {
-                const float4 x0 = *reinterpret_cast<const float4*>(xr + j);
-                const float4 x1 = *reinterpret_cast<const float4*>(xr + j + 4);
-                f[0] += x0.x; f[1] += x0.y; f[2] += x0.z; f[3] += x0.w;
-                f[4] += x1.x; f[5] += x1.y; f[6] += x1.z; f[7] += x1.w;
-              }
-#pragma unroll
-              for (int q = 0; q < 8; ++q) ss = fmaf(f[q], f[q], ss);
-              *reinterpret_cast<float4*>(xr + j) = make_float4(f[0], f[1], f[2], f[3]);
-              *reinterpret_cast<float4*>(xr + j + 4) = make_float4(f[4], f[5], f[6], f[7]);
-              const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.norm_w + n0 + c + j));
-              const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.norm_w + n0 + c + j + 4));
-              *reinterpret_cast<uint4*>(xb + j) =
-                  make_uint4(pack_bf16x2(f[0] * w0.x, f[1] * w0.y), pack_bf16x2(f[2] * w0.z, f[3] * w0.w),
-                             pack_bf16x2(f[4] * w1.x, f[5] * w1.y), pack_bf16x2(f[6] * w1.z, f[7] * w1.w));
+          for (int j = 0; j < 16; j += 4) {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + j));
+            float4 xo = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.flags & GEMM_ADD_RESID) {
+              if (direct) { if (valid) xo = *reinterpret_cast<const float4*>(p.x + dest * p.ldx + n0 + c + j); }
+              else xo = *st.f4(lane, j >> 2);
             }
+            f[j] = __uint_as_float(v[j]) + b.x + xo.x;
+            f[j + 1] = __uint_as_float(v[j + 1]) + b.y + xo.y;
+            f[j + 2] = __uint_as_float(v[j + 2]) + b.z + xo.z;
+            f[j + 3] = __uint_as_float(v[j + 3]) + b.w + xo.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) ss = fmaf(f[j], f[j], ss);
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 w = __ldg(reinterpret_cast<const float4*>(p.norm_w + n0 + c + j));
+            pk[j >> 1] = pack_bf16x2(f[j] * w.x, f[j + 1] * w.y);
+            pk[(j >> 1) + 1] = pack_bf16x2(f[j + 2] * w.z, f[j + 3] * w.w);
+          }
+          if (direct) {
+            if (valid) {
+              float* xr = p.x + dest * p.ldx + n0 + c;
+              __nv_bfloat16* xb = p.out_bf16 + dest * p.ld_out + n0 + c;
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(xr + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              *reinterpret_cast<uint4*>(xb) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              *reinterpret_cast<uint4*>(xb + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *st.f4(lane, j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            __syncwarp();
+            st.store_f32(xg, p.ldx, rows_valid, lane);
+            __syncwarp();
+            *st.h8(lane, 0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            *st.h8(lane, 1) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            __syncwarp();
+            st.store_bf16(p.out_bf16 + static_cast<int64_t>(row0) * p.ld_out + n0 + c, p.ld_out, rows_valid, lane);
+            __syncwarp();
           }
         }
-        if (valid) p.ssq[dest * num_n_blocks + n_blk] = ss;
+        // one partial per (row, 64-column group): deterministic, no atomics
+        if (valid) p.ssq[dest * (num_n_blocks * C::groups) + n_blk * C::groups + cg] = ss;
       } else if constexpr (EPI == EPI_QKV) {
-        // Tile = 3 heads of 80; rotary pairs (d, d+40) live in the same thread's row.
+        // Tile = 3 heads of 80, one head per column group; rotary pairs (d, d+40) live in one thread's row.
         float rstd = 0.f;
         if (valid) {
           float s = 0.f;
-          for (int q = 0; q < p.ssq_parts; ++q) s += p.ssq_in[static_cast<int64_t>(r) * p.ssq_parts + q];
+          const float* sp = p.ssq_in + static_cast<int64_t>(r) * p.ssq_parts;
+          for (int q = 0; q < p.ssq_parts; q += 4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(sp + q);
+            s += (t4.x + t4.y) + (t4.z + t4.w);
+          }
           rstd = rsqrtf(s * p.inv_dim + p.eps);
         }
+        const int col0 = n0 + cg * 80;
+        const bool rot = col0 < 2 * (p.N / 3);  // q and k heads rotate, v heads do not
+        __nv_bfloat16* og = p.out_bf16 + static_cast<int64_t>(row0) * p.ld_out + col0;   // head origin, this warp's rows
 #pragma unroll 1
-        for (int hd = 0; hd < BN / 80; ++hd) {
-          const int col0 = n0 + hd * 80;
-          const bool rot = col0 < 2 * (p.N / 3);  // q and k heads rotate, v heads do not
-#pragma unroll 1
-          for (int i0 = 0; i0 < 40; i0 += 8) {
-            uint32_t lo[8], hi[8];
-            tmem_ld8(taddr + hd * 80 + i0, lo);
-            tmem_ld8(taddr + hd * 80 + 40 + i0, hi);
-            tmem_ld_wait();
-            if (valid) {
-              float a[8], b[8];
+        for (int i0 = 0; i0 < 40; i0 += 16) {
+          const int wdt = (40 - i0) < 16 ? 8 : 16;   // 16, 16, 8 pairs
+          uint32_t lo[16], hi[16];
+          tmem_ld8(taddr + cg * 80 + i0, lo);
+          tmem_ld8(taddr + cg * 80 + 40 + i0, hi);
+          if (wdt == 16) {
+            tmem_ld8(taddr + cg * 80 + i0 + 8, lo + 8);
+            tmem_ld8(taddr + cg * 80 + 40 + i0 + 8, hi + 8);
+          }
+          float cs[16], sn[16];
+          if (rot) {
+            // cos / sin rows of this warp's 32 patches, pulled through the staging buffer row-contiguously
+            st.load_f32_w(p.cos_tab + static_cast<int64_t>(row0) * 40 + i0, 40, rows_valid, lane, wdt);
+            __syncwarp();
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                a[q] = fmaf(__uint_as_float(lo[q]), rstd, __ldg(p.bias + col0 + i0 + q));
-                b[q] = fmaf(__uint_as_float(hi[q]), rstd, __ldg(p.bias + col0 + 40 + i0 + q));
-              }
-              if (rot) {
-                const float* cr = p.cos_tab + static_cast<int64_t>(r) * 40 + i0;
-                const float* sr = p.sin_tab + static_cast<int64_t>(r) * 40 + i0;
-                const float4 c0 = *reinterpret_cast<const float4*>(cr);
-                const float4 c1 = *reinterpret_cast<const float4*>(cr + 4);
-                const float4 s0 = *reinterpret_cast<const float4*>(sr);
-                const float4 s1 = *reinterpret_cast<const float4*>(sr + 4);
-                const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-                const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+            for (int j = 0; j < 4; ++j) {
+              const float4 t4 = *st.f4(lane, j);
+              cs[4 * j] = t4.x; cs[4 * j + 1] = t4.y; cs[4 * j + 2] = t4.z; cs[4 * j + 3] = t4.w;
+            }
+            __syncwarp();
+            st.load_f32_w(p.sin_tab + static_cast<int64_t>(row0) * 40 + i0, 40, rows_valid, lane, wdt);
+            __syncwarp();
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                  // q*cos + rotate_half(q)*sin, fp32 (HF :161-166), no FMA contraction surprises needed
-                  const float na = a[q] * cs[q] - b[q] * sn[q];
-                  const float nb = b[q] * cs[q] + a[q] * sn[q];
-                  a[q] = na;
-                  b[q] = nb;
-                }
-              }
-              __nv_bfloat16* o = p.out_bf16 + static_cast<int64_t>(r) * p.ld_out + col0 + i0;
-              *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]),
-                                                        pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
-              *reinterpret_cast<uint4*>(o + 40) = make_uint4(pack_bf16x2(b[0], b[1]), pack_bf16x2(b[2], b[3]),
-                                                             pack_bf16x2(b[4], b[5]), pack_bf16x2(b[6], b[7]));
+            for (int j = 0; j < 4; ++j) {
+              const float4 t4 = *st.f4(lane, j);
+              sn[4 * j] = t4.x; sn[4 * j + 1] = t4.y; sn[4 * j + 2] = t4.z; sn[4 * j + 3] = t4.w;
+            }
+            __syncwarp();
+          }
+          tmem_ld_wait();
+          float a[16], b[16];
+#pragma unroll
+          for (int q = 0; q < 16; q += 4) {
+            if (q < wdt) {
+              const float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i0 + q));
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 40 + i0 + q));
+              a[q] = fmaf(__uint_as_float(lo[q]), rstd, ba.x);
+              a[q + 1] = fmaf(__uint_as_float(lo[q + 1]), rstd, ba.y);
+              a[q + 2] = fmaf(__uint_as_float(lo[q + 2]), rstd, ba.z);
+              a[q + 3] = fmaf(__uint_as_float(lo[q + 3]), rstd, ba.w);
+              b[q] = fmaf(__uint_as_float(hi[q]), rstd, bb.x);
+              b[q + 1] = fmaf(__uint_as_float(hi[q + 1]), rstd, bb.y);
+              b[q + 2] = fmaf(__uint_as_float(hi[q + 2]), rstd, bb.z);
+              b[q + 3] = fmaf(__uint_as_float(hi[q + 3]), rstd, bb.w);
+            } else {
+              a[q] = a[q + 1] = a[q + 2] = a[q + 3] = 0.f;
+              b[q] = b[q + 1] = b[q + 2] = b[q + 3] = 0.f;
             }
           }
+          if (rot) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              // q*cos + rotate_half(q)*sin in fp32 (HF :161-166)
+              const float na = a[q] * cs[q] - b[q] * sn[q];
+              const float nb = b[q] * cs[q] + a[q] * sn[q];
+              a[q] = na;
+              b[q] = nb;
+            }
+          }
+          // lo half -> columns [i0, i0+wdt), hi half -> [40+i0, 40+i0+wdt)
+          *st.h8(lane, 0) = make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
+          *st.h8(lane, 1) = make_uint4(pack_bf16x2(a[8], a[9]), pack_bf16x2(a[10], a[11]), pack_bf16x2(a[12], a[13]), pack_bf16x2(a[14], a[15]));
+          __syncwarp();
+          st.store_bf16_w(og + i0, p.ld_out, rows_valid, lane, wdt);
+          __syncwarp();
+          *st.h8(lane, 0) = make_uint4(pack_bf16x2(b[0], b[1]), pack_bf16x2(b[2], b[3]), pack_bf16x2(b[4], b[5]), pack_bf16x2(b[6], b[7]));
+          *st.h8(lane, 1) = make_uint4(pack_bf16x2(b[8], b[9]), pack_bf16x2(b[10], b[11]), pack_bf16x2(b[12], b[13]), pack_bf16x2(b[14], b[15]));
+          __syncwarp();
+          st.store_bf16_w(og + 40 + i0, p.ld_out, rows_valid, lane, wdt);
+          __syncwarp();
         }
       } else if constexpr (EPI == EPI_SWIGLU) {
-        // Tile columns [0,128) are gate rows, [128,256) the matching up rows.
+        // Tile columns [0,128) are gate rows, [128,256) the matching up rows; group cg owns 32 outputs.
         float rstd = 0.f;
         if (valid) {
           float s = 0.f;
-          for (int q = 0; q < p.ssq_parts; ++q) s += p.ssq_in[static_cast<int64_t>(r) * p.ssq_parts + q];
+          const float* sp = p.ssq_in + static_cast<int64_t>(r) * p.ssq_parts;
+          for (int q = 0; q < p.ssq_parts; q += 4) {
+            const float4 t4 = *reinterpret_cast<const float4*>(sp + q);
+            s += (t4.x + t4.y) + (t4.z + t4.w);
+          }
           rstd = rsqrtf(s * p.inv_dim + p.eps);
         }
+        constexpr int OC = BN / 2 / C::groups;  // 32 output columns per group
 #pragma unroll 1
-        for (int c = 0; c < BN / 2; c += 16) {
+        for (int c = cg * OC; c < (cg + 1) * OC; c += 16) {
           uint32_t g[16], u[16];
           tmem_ld16(taddr + c, g);
           tmem_ld16(taddr + BN / 2 + c, u);
           tmem_ld_wait();
-          if (valid) {
-            float h[16];
+          float h[16];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-              const float gv = fmaf(__uint_as_float(g[q]), rstd, __ldg(p.bias + n0 + c + q));
-              const float uv = fmaf(__uint_as_float(u[q]), rstd, __ldg(p.bias + n0 + BN / 2 + c + q));
-              h[q] = silu(gv) * uv;
-            }
-            __nv_bfloat16* o = p.out_bf16 + static_cast<int64_t>(r) * p.ld_out + n_blk * (BN / 2) + c;
-            *reinterpret_cast<uint4*>(o) = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]),
-                                                      pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
-            *reinterpret_cast<uint4*>(o + 8) = make_uint4(pack_bf16x2(h[8], h[9]), pack_bf16x2(h[10], h[11]),
-                                                          pack_bf16x2(h[12], h[13]), pack_bf16x2(h[14], h[15]));
+          for (int q = 0; q < 16; q += 4) {
+            const float4 bg = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + q));
+            const float4 bu = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + BN / 2 + c + q));
+            h[q] = silu(fmaf(__uint_as_float(g[q]), rstd, bg.x)) * fmaf(__uint_as_float(u[q]), rstd, bu.x);
+            h[q + 1] = silu(fmaf(__uint_as_float(g[q + 1]), rstd, bg.y)) * fmaf(__uint_as_float(u[q + 1]), rstd, bu.y);
+            h[q + 2] = silu(fmaf(__uint_as_float(g[q + 2]), rstd, bg.z)) * fmaf(__uint_as_float(u[q + 2]), rstd, bu.z);
+            h[q + 3] = silu(fmaf(__uint_as_float(g[q + 3]), rstd, bg.w)) * fmaf(__uint_as_float(u[q + 3]), rstd, bu.w);
           }
+          *st.h8(lane, 0) = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+          *st.h8(lane, 1) = make_uint4(pack_bf16x2(h[8], h[9]), pack_bf16x2(h[10], h[11]), pack_bf16x2(h[12], h[13]), pack_bf16x2(h[14], h[15]));
+          __syncwarp();
+          st.store_bf16(p.out_bf16 + static_cast<int64_t>(row0) * p.ld_out + n_blk * (BN / 2) + c, p.ld_out, rows_valid, lane);
+          __syncwarp();
         }
       }
       // all of this warp's TMEM reads are complete (tcgen05.wait::ld above)
@@ -320,7 +489,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -358,7 +527,7 @@ cudaError_t launch(const GemmArgs& a, int num_sms, cudaStream_t stream, const ch
   }
   const int tiles = ((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_kernel<BN, EPI><<<grid, kThreads, C::smem_bytes, stream>>>(tmA, tmB, a);
+  gemm_kernel<BN, EPI><<<grid, C::threads, C::smem_bytes, stream>>>(tmA, tmB, a);
   return cudaGetLastError();
 }
 
@@ -396,8 +565,8 @@ cudaError_t gemm_launch(const GemmArgs& a, int num_sms, cudaStream_t stream, con
         *err = "gemm: missing output";
         return cudaErrorInvalidValue;
       }
-      if (a.N % 8 != 0) {
-        *err = "gemm: EPI_STORE needs N % 8 == 0";
+      if (a.N % 32 != 0) {
+        *err = "gemm: EPI_STORE needs N % 32 == 0";
         return cudaErrorInvalidValue;
       }
       return launch<256, EPI_STORE>(a, num_sms, stream, err);
@@ -408,14 +577,14 @@ cudaError_t gemm_launch(const GemmArgs& a, int num_sms, cudaStream_t stream, con
       }
       return launch<256, EPI_RESID>(a, num_sms, stream, err);
     case EPI_QKV:
-      if (a.N % 240 != 0 || a.bias == nullptr || a.ssq_in == nullptr || a.cos_tab == nullptr ||
+      if (a.N % 240 != 0 || a.ssq_parts % 4 != 0 || a.bias == nullptr || a.ssq_in == nullptr || a.cos_tab == nullptr ||
           a.sin_tab == nullptr || a.out_bf16 == nullptr) {
         *err = "gemm: EPI_QKV needs N % 240 == 0 and bias/ssq/cos/sin/out";
         return cudaErrorInvalidValue;
       }
       return launch<240, EPI_QKV>(a, num_sms, stream, err);
     case EPI_SWIGLU:
-      if (a.N % 256 != 0 || a.bias == nullptr || a.ssq_in == nullptr || a.out_bf16 == nullptr) {
+      if (a.N % 256 != 0 || a.ssq_parts % 4 != 0 || a.bias == nullptr || a.ssq_in == nullptr || a.out_bf16 == nullptr) {
         *err = "gemm: EPI_SWIGLU needs N % 256 == 0 and bias/ssq/out";
         return cudaErrorInvalidValue;
       }

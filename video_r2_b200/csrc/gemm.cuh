@@ -40,7 +40,7 @@ struct GemmArgs {
   int64_t ld_out;
   const int* row_map;      // destination row of source row r (null = identity)
   const float* norm_w;     // EPI_RESID: weight of the RMSNorm that reads x next, [N]
-  float* ssq;              // partial sum of squares: written [rows, N/256] by EPI_RESID
+  float* ssq;              // partial sum of squares: written [rows, N/64] by EPI_RESID (one per 64-column group)
   const float* ssq_in;     // read by EPI_QKV / EPI_SWIGLU, [M, ssq_parts]
   int ssq_parts;
   float inv_dim;           // 1 / hidden

@@ -133,7 +133,7 @@ extern "C" int vr2_tower_create(const vr2_tower_config* cfg, int32_t device, vr2
   if (cfg->hidden_size % 256 != 0 || (3 * cfg->hidden_size) % 240 != 0)
     return fail(VR2_ERR_ARG, "vr2_tower_create: hidden_size %d must be a multiple of 1280", cfg->hidden_size);
   if (cfg->spatial_merge_size != 2) return fail(VR2_ERR_ARG, "vr2_tower_create: spatial_merge_size must be 2");
-  if (cfg->out_hidden_size % 8 != 0) return fail(VR2_ERR_ARG, "vr2_tower_create: out_hidden_size must be a multiple of 8");
+  if (cfg->out_hidden_size % 32 != 0) return fail(VR2_ERR_ARG, "vr2_tower_create: out_hidden_size must be a multiple of 32");
   if (cfg->n_fullatt < 0 || cfg->n_fullatt > 8) return fail(VR2_ERR_ARG, "vr2_tower_create: n_fullatt out of range");
   const int patch_k = cfg->in_channels * cfg->temporal_patch_size * cfg->patch_size * cfg->patch_size;
   if (patch_k % 8 != 0) return fail(VR2_ERR_ARG, "vr2_tower_create: patch row of %d elements is not 16-byte aligned", patch_k);
@@ -309,7 +309,7 @@ Workspace carve_ws(const vr2_tower* t, int64_t n, void* base) {
   w.qkv = reinterpret_cast<__nv_bfloat16*>(take(N * 3 * h * 2));
   w.att = reinterpret_cast<__nv_bfloat16*>(take(N * h * 2));
   w.hbuf = reinterpret_cast<__nv_bfloat16*>(take(N * std::max<size_t>(t->ipad, h) * 2));
-  w.ssq = reinterpret_cast<float*>(take(N * (h / 256) * 4));
+  w.ssq = reinterpret_cast<float*>(take(N * (h / 64) * 4));
   w.pix = reinterpret_cast<__nv_bfloat16*>(take(N * t->patch_k * 2));
   w.bytes = static_cast<size_t>(cur - static_cast<char*>(base));
   return w;
@@ -346,7 +346,7 @@ extern "C" int vr2_tower_forward(vr2_tower* t, const vr2_plan* plan, const void*
     return fail(VR2_ERR_ARG, "vr2_tower_forward: workspace %zu < required %zu bytes", workspace_bytes, w.bytes);
   cudaStream_t s = as_stream(stream_v);
   const int h = t->cfg.hidden_size;
-  const int parts = h / 256;
+  const int parts = h / 64;  // EPI_RESID writes one partial per 64-column group
   const float eps = t->cfg.rms_norm_eps;
   const char* msg = "";
   auto G = [&](const GemmArgs& a, int kind, const char* what) -> int {
