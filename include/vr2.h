@@ -117,6 +117,17 @@ typedef struct vr2_tower_config {
 } vr2_tower_config;
 
 int vr2_tower_create(const vr2_tower_config* cfg, int32_t cuda_device, vr2_tower** out);
+/* Operand precision of the dense contractions (GEMMs and attention); accumulation, residual stream, norms,
+ * rotary and softmax are fp32 in both.
+ *   VR2_PRECISION_BF16  (default): activations rounded to bf16 once per GEMM input — the arithmetic HF's own
+ *                        bf16 path uses (modeling_qwen2_5_vl.py under autocast / .to(bfloat16)).
+ *   VR2_PRECISION_SPLIT: every activation operand is carried as hi + lo bf16 (lo = rounding residual) and
+ *                        multiplied twice (3 products inside attention): ~16 mantissa bits, 2x the MMA work.
+ *                        This is the mode that meets max-abs 2e-2 against the fp32 reference on a 32-block tower.
+ * Changes vr2_tower_workspace_bytes(); call before sizing the workspace. */
+typedef enum vr2_precision { VR2_PRECISION_BF16 = 0, VR2_PRECISION_SPLIT = 1 } vr2_precision;
+int vr2_tower_set_precision(vr2_tower* tower, int32_t precision);
+int32_t vr2_tower_get_precision(const vr2_tower* tower);
 void vr2_tower_destroy(vr2_tower* tower);
 /* One call per entry of the HF module's state_dict (names relative to the
  * vision module: "patch_embed.proj.weight", "blocks.0.norm1.weight",
@@ -191,6 +202,9 @@ int vr2_rope_index(const vr2_rope_config* cfg, const int64_t* input_ids_dev, con
 /* C[M,N] = A[M,K] W[N,K]^T (+bias) (GELU optional); A, W bf16; out bf16 or fp32. */
 int vr2_op_linear(const void* a_dev, const void* w_dev, const float* bias_dev, void* out_dev, int32_t out_dtype,
                   int32_t M, int32_t N, int32_t K, int32_t gelu, void* stream);
+/* Split-operand variant: C = (A_hi + A_lo) W^T, A_lo bf16 with A's layout. */
+int vr2_op_linear_split(const void* a_hi_dev, const void* a_lo_dev, const void* w_dev, const float* bias_dev,
+                        void* out_dev, int32_t out_dtype, int32_t M, int32_t N, int32_t K, int32_t gelu, void* stream);
 /* out = bf16(x * rsqrt(mean(x^2)+eps) * w), x fp32 [rows, dim]. */
 int vr2_op_rmsnorm(const float* x_dev, const float* w_dev, void* out_bf16_dev, int64_t rows, int32_t dim, float eps,
                    void* stream);
@@ -198,6 +212,10 @@ int vr2_op_rmsnorm(const float* x_dev, const float* w_dev, void* out_bf16_dev, i
  * out bf16 [N, heads*80]. Synchronises the stream (test helper). */
 int vr2_op_attention(const void* qkv_dev, void* out_dev, const int32_t* cu_seqlens_host, int32_t n_seq,
                      int32_t num_heads, void* stream);
+
+/* Split-operand variant: q/k/v and the output are hi + lo bf16 pairs of the same layout. */
+int vr2_op_attention_split(const void* qkv_hi_dev, const void* qkv_lo_dev, void* out_hi_dev, void* out_lo_dev,
+                           const int32_t* cu_seqlens_host, int32_t n_seq, int32_t num_heads, void* stream);
 
 #ifdef __cplusplus
 }

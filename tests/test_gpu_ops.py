@@ -62,3 +62,44 @@ def test_attention_varlen_matches_fp32(lens):
     ref = _attn_ref(qkv, cu, heads)
     err = (out.float() - ref).abs().max().item()
     assert err < 2e-2, err  # P and the output are rounded to bf16
+
+
+# ------------------------------------------------------------------ "split" precision (hi + lo bf16 operands)
+@pytest.mark.parametrize("M,N,K", [(200, 288, 1176), (1000, 1280, 1280), (4096, 1280, 3456), (513, 3584, 5120)])
+def test_linear_split_matches_fp32(M, N, K):
+    """(A_hi + A_lo) W^T against an fp64 reference of the UNROUNDED fp32 activations: the split operand keeps
+    ~16 mantissa bits, so the error is two orders below the plain bf16 GEMM on the same input."""
+    from video_r2_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    a32 = torch.randn(M, K, generator=g).cuda()
+    w = _bf16((N, K), 12, scale=0.05)
+    hi, lo = ops.split_bf16(a32)
+    ref = (a32.double() @ w.double().T).float()
+    out_split = ops.linear(hi, w, a_lo=lo)
+    out_plain = ops.linear(hi, w)
+    e_split = (out_split - ref).abs().max().item()
+    e_plain = (out_plain - ref).abs().max().item()
+    print(f"\nsplit {e_split:.2e}  plain {e_plain:.2e}")
+    assert e_split < 1e-3 * math.sqrt(K / 64), e_split   # fp32 accumulation order only
+    assert e_split * 20 < e_plain
+    # bf16-exact activations: lo == 0 and the two kernels agree bit for bit
+    z = torch.zeros_like(hi)
+    assert torch.equal(ops.linear(hi, w, a_lo=z), out_plain)
+
+
+@pytest.mark.parametrize("lens", [[64] * 6, [4, 16, 64, 32, 8, 48, 12], [1008, 720], [100, 1, 63, 65, 129]])
+def test_attention_split_matches_fp32(lens):
+    from video_r2_b200 import ops
+    heads = 16
+    cu = [0]
+    for L in lens:
+        cu.append(cu[-1] + L)
+    g = torch.Generator().manual_seed(13)
+    qkv32 = torch.randn(cu[-1], 3 * heads * 80, generator=g).cuda()
+    hi, lo = ops.split_bf16(qkv32)
+    o_hi, o_lo = ops.attention(hi, cu, heads, qkv_lo=lo)
+    ref = _attn_ref(qkv32, cu, heads)
+    err = (o_hi.float() + o_lo.float() - ref).abs().max().item()
+    err_plain = (ops.attention(hi, cu, heads).float() - _attn_ref(qkv32, cu, heads)).abs().max().item()
+    print(f"\nsplit {err:.2e}  plain {err_plain:.2e}")
+    assert err < 3e-4, err

@@ -9,6 +9,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvr2.so")
 
 VR2_F32, VR2_BF16, VR2_I64, VR2_I32, VR2_U8 = 0, 1, 2, 3, 4
+VR2_PRECISION_BF16, VR2_PRECISION_SPLIT = 0, 1
+PRECISIONS = {"bf16": VR2_PRECISION_BF16, "split": VR2_PRECISION_SPLIT}
 
 
 class Vr2Error(RuntimeError):
@@ -73,6 +75,8 @@ SIGNATURES = {
     "vr2_tower_destroy": (None, [_P]),
     "vr2_tower_set_weight": (C.c_int, [_P, C.c_char_p, _P, C.c_int32, C.POINTER(C.c_int64), C.c_int32, _P]),
     "vr2_tower_finalize": (C.c_int, [_P]),
+    "vr2_tower_set_precision": (C.c_int, [_P, C.c_int32]),
+    "vr2_tower_get_precision": (C.c_int32, [_P]),
     "vr2_tower_workspace_bytes": (C.c_size_t, [_P, C.c_int64]),
     "vr2_tower_forward": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int32, _P, C.c_size_t, _P]),
     "vr2_tower_profile": (C.c_int, [_P, C.c_uint32]),
@@ -82,8 +86,10 @@ SIGNATURES = {
     "vr2_rope_index": (C.c_int, [C.POINTER(RopeConfig), _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, _P,
                                  C.c_int32, _P, _P, _P, _P, _P]),
     "vr2_op_linear": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "vr2_op_linear_split": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "vr2_op_rmsnorm": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_float, _P]),
     "vr2_op_attention": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.c_int32, C.c_int32, _P]),
+    "vr2_op_attention_split": (C.c_int, [_P, _P, _P, _P, C.POINTER(C.c_int32), C.c_int32, C.c_int32, _P]),
 }
 
 _lib = None

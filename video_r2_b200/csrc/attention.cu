@@ -58,12 +58,24 @@ __device__ __forceinline__ void load_tile(__nv_bfloat16 (*dst)[HDP], const __nv_
   }
 }
 
+// SPLIT ("precise" mode): q/k/v arrive as hi + lo bf16 pairs and the probabilities are
+// split the same way; S = Qh Kh + Qh Kl + Ql Kh and O += Ph Vh + Ph Vl + Pl Vh (the lo x lo terms are
+// below 2^-16 relative), so every operand carries ~16 mantissa bits at 3x the MMA work.
+using Tile = __nv_bfloat16 (*)[HDP];
+
+template <bool SPLIT>
 __global__ void __launch_bounds__(128)
-attn_varlen_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out,
+attn_varlen_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ qkv_lo,
+                   __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_lo,
                    const int4* __restrict__ tiles, int64_t ld_qkv, int64_t ld_out, int hidden, float scale_log2) {
-  __shared__ __align__(16) __nv_bfloat16 sQ[TQ][HDP];
-  __shared__ __align__(16) __nv_bfloat16 sK[TK][HDP];
-  __shared__ __align__(16) __nv_bfloat16 sV[TK][HDP];
+  extern __shared__ __align__(16) uint8_t attn_smem[];
+  constexpr int kTile = TQ * HDP * 2;
+  Tile sQ = reinterpret_cast<Tile>(attn_smem);
+  Tile sK = reinterpret_cast<Tile>(attn_smem + kTile);
+  Tile sV = reinterpret_cast<Tile>(attn_smem + 2 * kTile);
+  Tile sQl = reinterpret_cast<Tile>(attn_smem + 3 * kTile);   // SPLIT only
+  Tile sKl = reinterpret_cast<Tile>(attn_smem + 4 * kTile);
+  Tile sVl = reinterpret_cast<Tile>(attn_smem + 5 * kTile);
 
   const int4 tile = tiles[blockIdx.x];
   const int q_start = tile.x, q_len = tile.y, kv_start = tile.z, kv_len = tile.w;
@@ -75,9 +87,12 @@ attn_varlen_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
   const __nv_bfloat16* kbase = qkv + static_cast<int64_t>(kv_start) * ld_qkv + hidden + head * HD;
   const __nv_bfloat16* vbase = kbase + hidden;
 
+  const int64_t lo_off = SPLIT ? qkv_lo - qkv : 0;   // same layout, element offset between the two buffers
   load_tile(sQ, qbase, ld_qkv, q_len);
+  if constexpr (SPLIT) load_tile(sQl, qbase + lo_off, ld_qkv, q_len);
 
   uint32_t qf[HD / 16][4];
+  uint32_t ql[SPLIT ? HD / 16 : 1][4];
   float o[HD / 8][4];
 #pragma unroll
   for (int i = 0; i < HD / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
@@ -89,12 +104,21 @@ attn_varlen_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
     const int nk = min(TK, kv_len - kt);
     load_tile(sK, kbase + static_cast<int64_t>(kt) * ld_qkv, ld_qkv, nk);
     load_tile(sV, vbase + static_cast<int64_t>(kt) * ld_qkv, ld_qkv, nk);
+    if constexpr (SPLIT) {
+      load_tile(sKl, kbase + lo_off + static_cast<int64_t>(kt) * ld_qkv, ld_qkv, nk);
+      load_tile(sVl, vbase + lo_off + static_cast<int64_t>(kt) * ld_qkv, ld_qkv, nk);
+    }
     cp_async_wait_all();
     __syncthreads();
     if (kt == 0) {
 #pragma unroll
       for (int ks = 0; ks < HD / 16; ++ks)
         ldsm_x4(qf[ks], &sQ[warp * 16 + (lane & 15)][ks * 16 + (lane >> 4) * 8]);
+      if constexpr (SPLIT) {
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks)
+          ldsm_x4(ql[ks], &sQl[warp * 16 + (lane & 15)][ks * 16 + (lane >> 4) * 8]);
+      }
     }
 
     // S = Q K^T  (16 x 64 per warp)
@@ -109,6 +133,13 @@ attn_varlen_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
         ldsm_x4(b, &sK[j * 16 + (lane & 7) + (lane >> 4) * 8][ks * 16 + ((lane >> 3) & 1) * 8]);
         mma_bf16(s[2 * j], qf[ks], b[0], b[1]);
         mma_bf16(s[2 * j + 1], qf[ks], b[2], b[3]);
+        if constexpr (SPLIT) {
+          mma_bf16(s[2 * j], ql[ks], b[0], b[1]);
+          mma_bf16(s[2 * j + 1], ql[ks], b[2], b[3]);
+          ldsm_x4(b, &sKl[j * 16 + (lane & 7) + (lane >> 4) * 8][ks * 16 + ((lane >> 3) & 1) * 8]);
+          mma_bf16(s[2 * j], qf[ks], b[0], b[1]);
+          mma_bf16(s[2 * j + 1], qf[ks], b[2], b[3]);
+        }
       }
     }
 
@@ -160,17 +191,31 @@ attn_varlen_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
     // O += P V   (P: 16 x 64 bf16 from the S fragments, V: 64 x 80)
 #pragma unroll
     for (int ks = 0; ks < TK / 16; ++ks) {
-      uint32_t a[4];
-      a[0] = pack_bf16x2(s[2 * ks][0], s[2 * ks][1]);
-      a[1] = pack_bf16x2(s[2 * ks][2], s[2 * ks][3]);
-      a[2] = pack_bf16x2(s[2 * ks + 1][0], s[2 * ks + 1][1]);
-      a[3] = pack_bf16x2(s[2 * ks + 1][2], s[2 * ks + 1][3]);
+      uint32_t a[4], al[4];
+      if constexpr (SPLIT) {
+        split_bf16x2(s[2 * ks][0], s[2 * ks][1], a[0], al[0]);
+        split_bf16x2(s[2 * ks][2], s[2 * ks][3], a[1], al[1]);
+        split_bf16x2(s[2 * ks + 1][0], s[2 * ks + 1][1], a[2], al[2]);
+        split_bf16x2(s[2 * ks + 1][2], s[2 * ks + 1][3], a[3], al[3]);
+      } else {
+        a[0] = pack_bf16x2(s[2 * ks][0], s[2 * ks][1]);
+        a[1] = pack_bf16x2(s[2 * ks][2], s[2 * ks][3]);
+        a[2] = pack_bf16x2(s[2 * ks + 1][0], s[2 * ks + 1][1]);
+        a[3] = pack_bf16x2(s[2 * ks + 1][2], s[2 * ks + 1][3]);
+      }
 #pragma unroll
       for (int dn = 0; dn < HD / 16; ++dn) {
         uint32_t b[4];
         ldsm_x4_t(b, &sV[ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][dn * 16 + (lane >> 4) * 8]);
         mma_bf16(o[2 * dn], a, b[0], b[1]);
         mma_bf16(o[2 * dn + 1], a, b[2], b[3]);
+        if constexpr (SPLIT) {
+          mma_bf16(o[2 * dn], al, b[0], b[1]);
+          mma_bf16(o[2 * dn + 1], al, b[2], b[3]);
+          ldsm_x4_t(b, &sVl[ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8][dn * 16 + (lane >> 4) * 8]);
+          mma_bf16(o[2 * dn], a, b[0], b[1]);
+          mma_bf16(o[2 * dn + 1], a, b[2], b[3]);
+        }
       }
     }
   }
@@ -180,27 +225,54 @@ attn_varlen_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restr
   __syncwarp();
 #pragma unroll
   for (int i = 0; i < HD / 8; ++i) {
-    *reinterpret_cast<uint32_t*>(&sQ[warp * 16 + g][i * 8 + 2 * t]) = pack_bf16x2(o[i][0] * inv0, o[i][1] * inv0);
-    *reinterpret_cast<uint32_t*>(&sQ[warp * 16 + g + 8][i * 8 + 2 * t]) = pack_bf16x2(o[i][2] * inv1, o[i][3] * inv1);
+    uint32_t h0, h1, l0 = 0, l1 = 0;
+    if constexpr (SPLIT) {
+      split_bf16x2(o[i][0] * inv0, o[i][1] * inv0, h0, l0);
+      split_bf16x2(o[i][2] * inv1, o[i][3] * inv1, h1, l1);
+      *reinterpret_cast<uint32_t*>(&sQl[warp * 16 + g][i * 8 + 2 * t]) = l0;
+      *reinterpret_cast<uint32_t*>(&sQl[warp * 16 + g + 8][i * 8 + 2 * t]) = l1;
+    } else {
+      h0 = pack_bf16x2(o[i][0] * inv0, o[i][1] * inv0);
+      h1 = pack_bf16x2(o[i][2] * inv1, o[i][3] * inv1);
+    }
+    *reinterpret_cast<uint32_t*>(&sQ[warp * 16 + g][i * 8 + 2 * t]) = h0;
+    *reinterpret_cast<uint32_t*>(&sQ[warp * 16 + g + 8][i * 8 + 2 * t]) = h1;
   }
   __syncwarp();
   for (int idx = lane; idx < 16 * (HD / 8); idx += 32) {
     const int row = warp * 16 + idx / (HD / 8);
     const int ch = idx % (HD / 8);
-    if (row < q_len)
-      *reinterpret_cast<uint4*>(out + static_cast<int64_t>(q_start + row) * ld_out + head * HD + ch * 8) =
-          *reinterpret_cast<const uint4*>(&sQ[row][ch * 8]);
+    if (row < q_len) {
+      const int64_t off = static_cast<int64_t>(q_start + row) * ld_out + head * HD + ch * 8;
+      *reinterpret_cast<uint4*>(out + off) = *reinterpret_cast<const uint4*>(&sQ[row][ch * 8]);
+      if constexpr (SPLIT) *reinterpret_cast<uint4*>(out_lo + off) = *reinterpret_cast<const uint4*>(&sQl[row][ch * 8]);
+    }
   }
 }
 
 }  // namespace
 
-cudaError_t attention_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, const int4* tiles, int n_tiles,
-                             int num_heads, int64_t ld_qkv, int64_t ld_out, cudaStream_t stream) {
+cudaError_t attention_launch(const __nv_bfloat16* qkv, const __nv_bfloat16* qkv_lo, __nv_bfloat16* out,
+                             __nv_bfloat16* out_lo, const int4* tiles, int n_tiles, int num_heads, int64_t ld_qkv,
+                             int64_t ld_out, cudaStream_t stream) {
   if (n_tiles <= 0) return cudaSuccess;
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
   dim3 grid(n_tiles, num_heads);
-  attn_varlen_kernel<<<grid, 128, 0, stream>>>(qkv, out, tiles, ld_qkv, ld_out, num_heads * HD, scale_log2);
+  constexpr int kTile = TQ * HDP * 2;
+  if (qkv_lo != nullptr) {
+    if (out_lo == nullptr) return cudaErrorInvalidValue;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(attn_varlen_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 6 * kTile);
+      if (e != cudaSuccess) return e;
+      attr_set = true;
+    }
+    attn_varlen_kernel<true><<<grid, 128, 6 * kTile, stream>>>(qkv, qkv_lo, out, out_lo, tiles, ld_qkv, ld_out,
+                                                               num_heads * HD, scale_log2);
+  } else {
+    attn_varlen_kernel<false><<<grid, 128, 3 * kTile, stream>>>(qkv, nullptr, out, nullptr, tiles, ld_qkv, ld_out,
+                                                                num_heads * HD, scale_log2);
+  }
   return cudaGetLastError();
 }
 

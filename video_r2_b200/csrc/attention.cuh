@@ -7,7 +7,9 @@ namespace vr2 {
 
 // tiles[i] = (q_start, q_len<=64, kv_start, kv_len): one 64-row query tile and the
 // cu_seqlens segment it attends to.  qkv: [N, 3*hidden] bf16 (q | k | v, heads of 80).
-cudaError_t attention_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, const int4* tiles, int n_tiles,
-                             int num_heads, int64_t ld_qkv, int64_t ld_out, cudaStream_t stream);
+// qkv_lo / out_lo non-null selects the split ("precise") kernel: operands are hi + lo bf16 pairs of the same layout.
+cudaError_t attention_launch(const __nv_bfloat16* qkv, const __nv_bfloat16* qkv_lo, __nv_bfloat16* out,
+                             __nv_bfloat16* out_lo, const int4* tiles, int n_tiles, int num_heads, int64_t ld_qkv,
+                             int64_t ld_out, cudaStream_t stream);
 
 }  // namespace vr2

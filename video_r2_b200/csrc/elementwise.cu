@@ -13,17 +13,24 @@ namespace vr2 {
 
 namespace {
 
-__global__ void cast_f32_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, int64_t n_vec) {
+// dst_lo (optional) receives the rounding residual bf16(v - bf16(v)) for the split ("precise") GEMMs
+__global__ void cast_f32_bf16_kernel(const float4* __restrict__ src, uint2* __restrict__ dst, uint2* __restrict__ dst_lo,
+                                     int64_t n_vec) {
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const float4 v = __ldg(src + i);
-    dst[i] = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    uint32_t h0, h1, l0, l1;
+    split_bf16x2(v.x, v.y, h0, l0);
+    split_bf16x2(v.z, v.w, h1, l1);
+    dst[i] = make_uint2(h0, h1);
+    if (dst_lo != nullptr) dst_lo[i] = make_uint2(l0, l1);
   }
 }
 
 // one warp per row; dim % 128 == 0 (32 lanes x float4)
 __global__ void rmsnorm_bf16_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                    __nv_bfloat16* __restrict__ out, int64_t rows, int dim, float eps) {
+                                    __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_lo, int64_t rows,
+                                    int dim, float eps) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
@@ -38,10 +45,15 @@ __global__ void rmsnorm_bf16_kernel(const float* __restrict__ x, const float* __
     for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
     const float rstd = rsqrtf(ss / static_cast<float>(dim) + eps);
     uint2* orow = reinterpret_cast<uint2*>(out + row * dim);
+    uint2* lrow = out_lo != nullptr ? reinterpret_cast<uint2*>(out_lo + row * dim) : nullptr;
     for (int v = lane; v < dim / 4; v += 32) {
       const float4 a = xr[v];
       const float4 g = __ldg(reinterpret_cast<const float4*>(w) + v);
-      orow[v] = make_uint2(pack_bf16x2(a.x * rstd * g.x, a.y * rstd * g.y), pack_bf16x2(a.z * rstd * g.z, a.w * rstd * g.w));
+      uint32_t h0, h1, l0, l1;
+      split_bf16x2(a.x * rstd * g.x, a.y * rstd * g.y, h0, l0);
+      split_bf16x2(a.z * rstd * g.z, a.w * rstd * g.w, h1, l1);
+      orow[v] = make_uint2(h0, h1);
+      if (lrow != nullptr) lrow[v] = make_uint2(l0, l1);
     }
   }
 }
@@ -70,17 +82,19 @@ int grid_for(int64_t work_items, int threads) {
 
 }  // namespace
 
-cudaError_t cast_f32_to_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t stream) {
+cudaError_t cast_f32_to_bf16(const float* src, __nv_bfloat16* dst, __nv_bfloat16* dst_lo, int64_t n,
+                             cudaStream_t stream) {
   if (n % 4 != 0) return cudaErrorInvalidValue;
   cast_f32_bf16_kernel<<<grid_for(n / 4, 256), 256, 0, stream>>>(reinterpret_cast<const float4*>(src),
-                                                                  reinterpret_cast<uint2*>(dst), n / 4);
+                                                                  reinterpret_cast<uint2*>(dst),
+                                                                  reinterpret_cast<uint2*>(dst_lo), n / 4);
   return cudaGetLastError();
 }
 
-cudaError_t rmsnorm_to_bf16(const float* x, const float* w, __nv_bfloat16* out, int64_t rows, int dim, float eps,
-                            cudaStream_t stream) {
+cudaError_t rmsnorm_to_bf16(const float* x, const float* w, __nv_bfloat16* out, __nv_bfloat16* out_lo, int64_t rows,
+                            int dim, float eps, cudaStream_t stream) {
   if (dim % 4 != 0) return cudaErrorInvalidValue;
-  rmsnorm_bf16_kernel<<<grid_for(rows * 32, 256), 256, 0, stream>>>(x, w, out, rows, dim, eps);
+  rmsnorm_bf16_kernel<<<grid_for(rows * 32, 256), 256, 0, stream>>>(x, w, out, out_lo, rows, dim, eps);
   return cudaGetLastError();
 }
 

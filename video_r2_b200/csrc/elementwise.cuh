@@ -5,11 +5,13 @@
 
 namespace vr2 {
 
-cudaError_t cast_f32_to_bf16(const float* src, __nv_bfloat16* dst, int64_t n, cudaStream_t stream);
+// dst = bf16(src); dst_lo (nullable) = bf16(src - dst), the residual the split ("precise") GEMMs add back
+cudaError_t cast_f32_to_bf16(const float* src, __nv_bfloat16* dst, __nv_bfloat16* dst_lo, int64_t n,
+                             cudaStream_t stream);
 
-// out = bf16(x * rsqrt(mean(x^2) + eps) * w), one warp per row
-cudaError_t rmsnorm_to_bf16(const float* x, const float* w, __nv_bfloat16* out, int64_t rows, int dim, float eps,
-                            cudaStream_t stream);
+// out = bf16(x * rsqrt(mean(x^2) + eps) * w), one warp per row; out_lo (nullable) = its rounding residual
+cudaError_t rmsnorm_to_bf16(const float* x, const float* w, __nv_bfloat16* out, __nv_bfloat16* out_lo, int64_t rows,
+                            int dim, float eps, cudaStream_t stream);
 
 // dst[(r / blk) * blk_stride + offset + r % blk][c] = src[r][c]  (dtype converted);
 // dst must be zero-filled beforehand where padding is wanted.

@@ -36,13 +36,17 @@ constexpr int UK = 16;   // K per tcgen05.mma (bf16)
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
 
-template <int BN>
+// SPLIT ("precise" mode): the A operand arrives as two bf16 tensors A_hi + A_lo (lo = the rounding
+// residual of hi), both multiplied with the same W k-block into one accumulator: 2x the MMA work,
+// ~16 mantissa bits on the activations.
+template <int BN, bool SPLIT>
 struct Cfg {
   static constexpr int groups = BN == 240 ? 3 : 4;        // epilogue column groups
   static constexpr int epi_warps = 4 * groups;
   static constexpr int threads = (epi_warps + 2) * 32;
   static constexpr int group_cols = BN / groups;           // 64 (BN=256) or 80 (BN=240)
-  static constexpr int a_bytes = BM * BK * 2;
+  static constexpr int a_half = BM * BK * 2;               // one A tile (hi or lo)
+  static constexpr int a_bytes = a_half * (SPLIT ? 2 : 1);
   static constexpr int b_bytes = BN * BK * 2;
   static constexpr int stage_bytes = a_bytes + b_bytes;
   static constexpr int stages = (196 * 1024) / stage_bytes;
@@ -120,10 +124,54 @@ struct Stage {
 __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
 __device__ __forceinline__ float silu(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
-template <int BN, int EPI>
-__global__ void __launch_bounds__(Cfg<BN>::threads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
-  using C = Cfg<BN>;
+template <bool SPLIT>
+__device__ __forceinline__ void pack16(const float* f, uint32_t* hi, uint32_t* lo) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if constexpr (SPLIT) split_bf16x2(f[2 * j], f[2 * j + 1], hi[j], lo[j]);
+    else hi[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+  }
+}
+// This thread's row, 16 consecutive columns -> the bf16 piece whose (row0, column) origin is g (and its
+// rounding residual to g_lo), row-contiguous through the warp's staging tile.
+template <bool SPLIT>
+__device__ __forceinline__ void emit_piece(const Stage& st, const float* f, __nv_bfloat16* g, __nv_bfloat16* g_lo,
+                                           int64_t ld, int rows_valid, int lane, int width) {
+  uint32_t hi[8], lo[8];
+  pack16<SPLIT>(f, hi, lo);
+  *st.h8(lane, 0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *st.h8(lane, 1) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+  __syncwarp();
+  st.store_bf16_w(g, ld, rows_valid, lane, width);
+  __syncwarp();
+  if constexpr (SPLIT) {
+    *st.h8(lane, 0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *st.h8(lane, 1) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+    __syncwarp();
+    st.store_bf16_w(g_lo, ld, rows_valid, lane, width);
+    __syncwarp();
+  }
+}
+// Same piece, thread-per-row (scattered destination rows): o / o_lo point at this row's 16 columns.
+template <bool SPLIT>
+__device__ __forceinline__ void emit_row(const float* f, __nv_bfloat16* o, __nv_bfloat16* o_lo) {
+  uint32_t hi[8], lo[8];
+  pack16<SPLIT>(f, hi, lo);
+  *reinterpret_cast<uint4*>(o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(o + 8) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+  if constexpr (SPLIT) {
+    if (o_lo != nullptr) {
+      *reinterpret_cast<uint4*>(o_lo) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      *reinterpret_cast<uint4*>(o_lo + 8) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+    }
+  }
+}
+
+template <int BN, int EPI, bool SPLIT>
+__global__ void __launch_bounds__(Cfg<BN, SPLIT>::threads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+            const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
+  using C = Cfg<BN, SPLIT>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment in the shared window.
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -147,6 +195,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   constexpr int kMmaWarp = C::epi_warps + 1;
   if (warp == kProducerWarp && lane == 0) {
     tma_prefetch_desc(&tmA);
+    if constexpr (SPLIT) tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < C::stages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -182,6 +231,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           uint8_t* sb = sa + C::a_bytes;
           mbar_expect_tx(&full_bar[s], C::stage_bytes);
           tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, m0);
+          if constexpr (SPLIT) tma_load_2d(sa + C::a_half, &tmA2, &full_bar[s], kb * BK, m0);
           tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, n0);
         }
       }
@@ -210,6 +260,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint64_t da = umma_desc_sw128(a_addr + k * UK * 2);
             const uint64_t db = umma_desc_sw128(b_addr + k * UK * 2);
             umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          if constexpr (SPLIT) {
+#pragma unroll
+            for (int k = 0; k < BK / UK; ++k) {
+              const uint64_t da = umma_desc_sw128(a_addr + C::a_half + k * UK * 2);
+              const uint64_t db = umma_desc_sw128(b_addr + k * UK * 2);
+              umma_bf16(tmem_d, da, db, idesc, 1u);
+            }
           }
           umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
         }
@@ -280,20 +338,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               __syncwarp();
             }
           } else {
-            const uint4 p0 = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-            const uint4 p1 = make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15]));
+            const int64_t off = n0 + c;
             if (direct) {
-              if (valid) {
-                __nv_bfloat16* o = p.out_bf16 + dest * p.ld_out + n0 + c;
-                *reinterpret_cast<uint4*>(o) = p0;
-                *reinterpret_cast<uint4*>(o + 8) = p1;
-              }
+              if (valid) emit_row<SPLIT>(f, p.out_bf16 + dest * p.ld_out + off, p.out_lo ? p.out_lo + dest * p.ld_out + off : nullptr);
+            } else if (SPLIT && p.out_lo == nullptr) {
+              emit_piece<false>(st, f, p.out_bf16 + static_cast<int64_t>(row0) * p.ld_out + off, nullptr, p.ld_out, rows_valid, lane, 16);
             } else {
-              *st.h8(lane, 0) = p0;
-              *st.h8(lane, 1) = p1;
-              __syncwarp();
-              st.store_bf16(p.out_bf16 + static_cast<int64_t>(row0) * p.ld_out + n0 + c, p.ld_out, rows_valid, lane);
-              __syncwarp();
+              emit_piece<SPLIT>(st, f, p.out_bf16 + static_cast<int64_t>(row0) * p.ld_out + off,
+                                p.out_lo + static_cast<int64_t>(row0) * p.ld_out + off, p.ld_out, rows_valid, lane, 16);
             }
           }
         }
@@ -326,21 +378,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
 #pragma unroll
           for (int j = 0; j < 16; ++j) ss = fmaf(f[j], f[j], ss);
-          uint32_t pk[8];
+          float xw[16];   // x * w of the RMSNorm that reads x next: the next GEMM's A operand before rounding
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
             const float4 w = __ldg(reinterpret_cast<const float4*>(p.norm_w + n0 + c + j));
-            pk[j >> 1] = pack_bf16x2(f[j] * w.x, f[j + 1] * w.y);
-            pk[(j >> 1) + 1] = pack_bf16x2(f[j + 2] * w.z, f[j + 3] * w.w);
+            xw[j] = f[j] * w.x;
+            xw[j + 1] = f[j + 1] * w.y;
+            xw[j + 2] = f[j + 2] * w.z;
+            xw[j + 3] = f[j + 3] * w.w;
           }
           if (direct) {
             if (valid) {
               float* xr = p.x + dest * p.ldx + n0 + c;
-              __nv_bfloat16* xb = p.out_bf16 + dest * p.ld_out + n0 + c;
 #pragma unroll
               for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(xr + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-              *reinterpret_cast<uint4*>(xb) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              *reinterpret_cast<uint4*>(xb + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+              emit_row<SPLIT>(xw, p.out_bf16 + dest * p.ld_out + n0 + c, p.out_lo ? p.out_lo + dest * p.ld_out + n0 + c : nullptr);
             }
           } else {
 #pragma unroll
@@ -348,11 +400,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             __syncwarp();
             st.store_f32(xg, p.ldx, rows_valid, lane);
             __syncwarp();
-            *st.h8(lane, 0) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            *st.h8(lane, 1) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-            __syncwarp();
-            st.store_bf16(p.out_bf16 + static_cast<int64_t>(row0) * p.ld_out + n0 + c, p.ld_out, rows_valid, lane);
-            __syncwarp();
+            const int64_t off = static_cast<int64_t>(row0) * p.ld_out + n0 + c;
+            emit_piece<SPLIT>(st, xw, p.out_bf16 + off, p.out_lo + off, p.ld_out, rows_valid, lane, 16);
           }
         }
         // one partial per (row, 64-column group): deterministic, no atomics
@@ -432,17 +481,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               b[q] = nb;
             }
           }
-          // lo half -> columns [i0, i0+wdt), hi half -> [40+i0, 40+i0+wdt)
-          *st.h8(lane, 0) = make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
-          *st.h8(lane, 1) = make_uint4(pack_bf16x2(a[8], a[9]), pack_bf16x2(a[10], a[11]), pack_bf16x2(a[12], a[13]), pack_bf16x2(a[14], a[15]));
-          __syncwarp();
-          st.store_bf16_w(og + i0, p.ld_out, rows_valid, lane, wdt);
-          __syncwarp();
-          *st.h8(lane, 0) = make_uint4(pack_bf16x2(b[0], b[1]), pack_bf16x2(b[2], b[3]), pack_bf16x2(b[4], b[5]), pack_bf16x2(b[6], b[7]));
-          *st.h8(lane, 1) = make_uint4(pack_bf16x2(b[8], b[9]), pack_bf16x2(b[10], b[11]), pack_bf16x2(b[12], b[13]), pack_bf16x2(b[14], b[15]));
-          __syncwarp();
-          st.store_bf16_w(og + 40 + i0, p.ld_out, rows_valid, lane, wdt);
-          __syncwarp();
+          // first half -> columns [i0, i0+wdt), second half -> [40+i0, 40+i0+wdt)
+          __nv_bfloat16* og_lo = p.out_lo + static_cast<int64_t>(row0) * p.ld_out + col0;
+          emit_piece<SPLIT>(st, a, og + i0, og_lo + i0, p.ld_out, rows_valid, lane, wdt);
+          emit_piece<SPLIT>(st, b, og + 40 + i0, og_lo + 40 + i0, p.ld_out, rows_valid, lane, wdt);
         }
       } else if constexpr (EPI == EPI_SWIGLU) {
         // Tile columns [0,128) are gate rows, [128,256) the matching up rows; group cg owns 32 outputs.
@@ -473,11 +515,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             h[q + 2] = silu(fmaf(__uint_as_float(g[q + 2]), rstd, bg.z)) * fmaf(__uint_as_float(u[q + 2]), rstd, bu.z);
             h[q + 3] = silu(fmaf(__uint_as_float(g[q + 3]), rstd, bg.w)) * fmaf(__uint_as_float(u[q + 3]), rstd, bu.w);
           }
-          *st.h8(lane, 0) = make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
-          *st.h8(lane, 1) = make_uint4(pack_bf16x2(h[8], h[9]), pack_bf16x2(h[10], h[11]), pack_bf16x2(h[12], h[13]), pack_bf16x2(h[14], h[15]));
-          __syncwarp();
-          st.store_bf16(p.out_bf16 + static_cast<int64_t>(row0) * p.ld_out + n_blk * (BN / 2) + c, p.ld_out, rows_valid, lane);
-          __syncwarp();
+          const int64_t off = static_cast<int64_t>(row0) * p.ld_out + n_blk * (BN / 2) + c;
+          emit_piece<SPLIT>(st, h, p.out_bf16 + off, p.out_lo + off, p.ld_out, rows_valid, lane, 16);
         }
       }
       // all of this warp's TMEM reads are complete (tcgen05.wait::ld above)
@@ -509,26 +548,33 @@ EncodeFn resolve_encode() {
   return fn;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool SPLIT>
 cudaError_t launch(const GemmArgs& a, int num_sms, cudaStream_t stream, const char** err) {
-  using C = Cfg<BN>;
-  CUtensorMap tmA, tmB;
+  using C = Cfg<BN, SPLIT>;
+  CUtensorMap tmA, tmA2, tmB;
   if (!tma_encode_2d_bf16(&tmA, a.A, a.K, a.M, a.lda * 2, BK, BM) ||
+      !tma_encode_2d_bf16(&tmA2, SPLIT ? a.A_lo : a.A, a.K, a.M, a.lda * 2, BK, BM) ||
       !tma_encode_2d_bf16(&tmB, a.W, a.K, a.N, a.ldw * 2, BK, BN)) {
     *err = "cuTensorMapEncodeTiled failed (alignment or driver entry point)";
     return cudaErrorInvalidValue;
   }
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, EPI, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          C::smem_bytes);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   const int tiles = ((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_kernel<BN, EPI><<<grid, C::threads, C::smem_bytes, stream>>>(tmA, tmB, a);
+  gemm_kernel<BN, EPI, SPLIT><<<grid, C::threads, C::smem_bytes, stream>>>(tmA, tmA2, tmB, a);
   return cudaGetLastError();
+}
+
+template <int BN, int EPI>
+cudaError_t launch_any(const GemmArgs& a, int num_sms, cudaStream_t stream, const char** err) {
+  return a.A_lo != nullptr ? launch<BN, EPI, true>(a, num_sms, stream, err)
+                           : launch<BN, EPI, false>(a, num_sms, stream, err);
 }
 
 }  // namespace
@@ -559,6 +605,16 @@ cudaError_t gemm_launch(const GemmArgs& a, int num_sms, cudaStream_t stream, con
     *err = "gemm: operand rows must be 16-byte aligned for TMA";
     return cudaErrorInvalidValue;
   }
+  if (a.A_lo != nullptr) {
+    if (reinterpret_cast<uintptr_t>(a.A_lo) & 15) {
+      *err = "gemm: A_lo must be 16-byte aligned for TMA";
+      return cudaErrorInvalidValue;
+    }
+    if (a.epilogue != EPI_STORE && a.out_lo == nullptr) {
+      *err = "gemm: split (A_hi + A_lo) GEMM needs out_lo for this epilogue";
+      return cudaErrorInvalidValue;
+    }
+  }
   switch (a.epilogue) {
     case EPI_STORE:
       if ((a.flags & GEMM_OUT_F32) ? a.out_f32 == nullptr : a.out_bf16 == nullptr) {
@@ -569,26 +625,26 @@ cudaError_t gemm_launch(const GemmArgs& a, int num_sms, cudaStream_t stream, con
         *err = "gemm: EPI_STORE needs N % 32 == 0";
         return cudaErrorInvalidValue;
       }
-      return launch<256, EPI_STORE>(a, num_sms, stream, err);
+      return launch_any<256, EPI_STORE>(a, num_sms, stream, err);
     case EPI_RESID:
       if (a.N % 256 != 0 || a.x == nullptr || a.out_bf16 == nullptr || a.norm_w == nullptr || a.ssq == nullptr) {
         *err = "gemm: EPI_RESID needs N % 256 == 0 and x/xb/norm_w/ssq";
         return cudaErrorInvalidValue;
       }
-      return launch<256, EPI_RESID>(a, num_sms, stream, err);
+      return launch_any<256, EPI_RESID>(a, num_sms, stream, err);
     case EPI_QKV:
       if (a.N % 240 != 0 || a.ssq_parts % 4 != 0 || a.bias == nullptr || a.ssq_in == nullptr || a.cos_tab == nullptr ||
           a.sin_tab == nullptr || a.out_bf16 == nullptr) {
         *err = "gemm: EPI_QKV needs N % 240 == 0 and bias/ssq/cos/sin/out";
         return cudaErrorInvalidValue;
       }
-      return launch<240, EPI_QKV>(a, num_sms, stream, err);
+      return launch_any<240, EPI_QKV>(a, num_sms, stream, err);
     case EPI_SWIGLU:
       if (a.N % 256 != 0 || a.ssq_parts % 4 != 0 || a.bias == nullptr || a.ssq_in == nullptr || a.out_bf16 == nullptr) {
         *err = "gemm: EPI_SWIGLU needs N % 256 == 0 and bias/ssq/out";
         return cudaErrorInvalidValue;
       }
-      return launch<256, EPI_SWIGLU>(a, num_sms, stream, err);
+      return launch_any<256, EPI_SWIGLU>(a, num_sms, stream, err);
     default:
       *err = "gemm: unknown epilogue";
       return cudaErrorInvalidValue;

@@ -25,6 +25,7 @@ enum GemmFlags : int {
 struct GemmArgs {
   // operands (device pointers, bf16, row-major, leading dimension in elements)
   const __nv_bfloat16* A;
+  const __nv_bfloat16* A_lo;   // non-null selects the split ("precise") GEMM: C = (A + A_lo) W^T, same layout as A
   int64_t lda;
   const __nv_bfloat16* W;
   int64_t ldw;
@@ -36,6 +37,7 @@ struct GemmArgs {
   float* x;                // EPI_RESID: residual stream fp32 [rows, ldx]
   int64_t ldx;
   __nv_bfloat16* out_bf16; // bf16 output (EPI_STORE / xb of EPI_RESID / qkv / h)
+  __nv_bfloat16* out_lo;   // split mode: rounding residual of out_bf16 (same layout); optional for EPI_STORE
   float* out_f32;          // EPI_STORE fp32 output
   int64_t ld_out;
   const int* row_map;      // destination row of source row r (null = identity)

@@ -60,6 +60,7 @@ struct vr2_tower {
   int patch_k = 1176;     // in_channels * temporal_patch * patch * patch
   int merge_dim = 5120;   // hidden * merge^2
   bool finalized = false;
+  int precision = VR2_PRECISION_BF16;
   std::vector<vr2::Layer> layers;
   vr2::Tensor patch_w;             // bf16 [h, patch_k]
   vr2::Tensor lnq_w;               // fp32 [h]
@@ -295,6 +296,12 @@ struct Workspace {
   __nv_bfloat16* hbuf;  // also the merger's hidden [N/4, 4h]
   float* ssq;
   __nv_bfloat16* pix;
+  // VR2_PRECISION_SPLIT: rounding residuals of the buffers above (same layouts), else null
+  __nv_bfloat16* xb_lo = nullptr;
+  __nv_bfloat16* qkv_lo = nullptr;
+  __nv_bfloat16* att_lo = nullptr;
+  __nv_bfloat16* hbuf_lo = nullptr;
+  __nv_bfloat16* pix_lo = nullptr;
   size_t bytes;
 };
 
@@ -311,6 +318,13 @@ Workspace carve_ws(const vr2_tower* t, int64_t n, void* base) {
   w.hbuf = reinterpret_cast<__nv_bfloat16*>(take(N * std::max<size_t>(t->ipad, h) * 2));
   w.ssq = reinterpret_cast<float*>(take(N * (h / 64) * 4));
   w.pix = reinterpret_cast<__nv_bfloat16*>(take(N * t->patch_k * 2));
+  if (t->precision == VR2_PRECISION_SPLIT) {
+    w.xb_lo = reinterpret_cast<__nv_bfloat16*>(take(N * h * 2));
+    w.qkv_lo = reinterpret_cast<__nv_bfloat16*>(take(N * 3 * h * 2));
+    w.att_lo = reinterpret_cast<__nv_bfloat16*>(take(N * h * 2));
+    w.hbuf_lo = reinterpret_cast<__nv_bfloat16*>(take(N * std::max<size_t>(t->ipad, h) * 2));
+    w.pix_lo = reinterpret_cast<__nv_bfloat16*>(take(N * t->patch_k * 2));
+  }
   w.bytes = static_cast<size_t>(cur - static_cast<char*>(base));
   return w;
 }
@@ -324,7 +338,7 @@ extern "C" size_t vr2_tower_workspace_bytes(const vr2_tower* t, int64_t n_patche
 
 extern "C" int64_t vr2_tower_launch_count(const vr2_tower* t, const vr2_plan* plan, int32_t pixels_dtype) {
   if (t == nullptr || plan == nullptr) return -1;
-  return (pixels_dtype == VR2_F32 ? 1 : 0) + 1 + 5 * static_cast<int64_t>(t->cfg.depth) + 3;
+  return (pixels_dtype == VR2_F32 ? 1 : 0) + 1 + 5 * static_cast<int64_t>(t->cfg.depth) + 3;  // memset is not a kernel
 }
 
 extern "C" int vr2_tower_forward(vr2_tower* t, const vr2_plan* plan, const void* pixels, int32_t pixels_dtype,
@@ -358,18 +372,21 @@ extern "C" int vr2_tower_forward(vr2_tower* t, const vr2_plan* plan, const void*
   int rc;
 
   // ---- patch embed (Conv3d with kernel == stride == a [N,1176] x [1176,1280] GEMM), stored window-permuted
+  const bool split = t->precision == VR2_PRECISION_SPLIT;
   const __nv_bfloat16* pix = static_cast<const __nv_bfloat16*>(pixels);
   if (pixels_dtype == VR2_F32) {
     ProfScope prof(t, VR2_K_CAST, s);
-    VR2_CUDA(cast_f32_to_bf16(static_cast<const float*>(pixels), w.pix, N * t->patch_k, s));
+    VR2_CUDA(cast_f32_to_bf16(static_cast<const float*>(pixels), w.pix, w.pix_lo, N * t->patch_k, s));
     pix = w.pix;
+  } else if (split) {
+    VR2_CUDA(cudaMemsetAsync(w.pix_lo, 0, static_cast<size_t>(N) * t->patch_k * 2, s));  // bf16 pixels: no residual
   }
   {
     GemmArgs a{};
-    a.A = pix; a.lda = t->patch_k; a.W = static_cast<const __nv_bfloat16*>(t->patch_w.ptr); a.ldw = t->patch_k;
+    a.A = pix; a.A_lo = w.pix_lo; a.lda = t->patch_k; a.W = static_cast<const __nv_bfloat16*>(t->patch_w.ptr); a.ldw = t->patch_k;
     a.M = static_cast<int>(N); a.N = h; a.K = t->patch_k;
     a.epilogue = EPI_RESID; a.flags = 0;
-    a.x = w.x; a.ldx = h; a.out_bf16 = w.xb; a.ld_out = h;
+    a.x = w.x; a.ldx = h; a.out_bf16 = w.xb; a.out_lo = w.xb_lo; a.ld_out = h;
     a.row_map = plan->row_map;
     a.norm_w = static_cast<const float*>(t->layers[0].norm1_w.ptr);
     a.ssq = w.ssq;
@@ -380,11 +397,11 @@ extern "C" int vr2_tower_forward(vr2_tower* t, const vr2_plan* plan, const void*
     const Layer& L = t->layers[l];
     {
       GemmArgs a{};
-      a.A = w.xb; a.lda = h; a.W = static_cast<const __nv_bfloat16*>(L.qkv_w.ptr); a.ldw = h;
+      a.A = w.xb; a.A_lo = w.xb_lo; a.lda = h; a.W = static_cast<const __nv_bfloat16*>(L.qkv_w.ptr); a.ldw = h;
       a.M = static_cast<int>(N); a.N = 3 * h; a.K = h;
       a.epilogue = EPI_QKV;
       a.bias = static_cast<const float*>(L.qkv_b.ptr);
-      a.out_bf16 = w.qkv; a.ld_out = 3 * h;
+      a.out_bf16 = w.qkv; a.out_lo = w.qkv_lo; a.ld_out = 3 * h;
       a.ssq_in = w.ssq; a.ssq_parts = parts; a.inv_dim = 1.0f / h; a.eps = eps;
       a.cos_tab = plan->cos_tab; a.sin_tab = plan->sin_tab;
       if ((rc = G(a, VR2_K_QKV, "qkv")) != VR2_OK) return rc;
@@ -392,38 +409,38 @@ extern "C" int vr2_tower_forward(vr2_tower* t, const vr2_plan* plan, const void*
     {
       const bool full = is_full_layer(t, l);
       ProfScope prof(t, full ? VR2_K_ATTN_FULL : VR2_K_ATTN_WINDOW, s);
-      VR2_CUDA(attention_launch(w.qkv, w.att, full ? plan->tiles_full : plan->tiles_window,
+      VR2_CUDA(attention_launch(w.qkv, w.qkv_lo, w.att, w.att_lo, full ? plan->tiles_full : plan->tiles_window,
                                 static_cast<int>(full ? plan->n_tiles_full : plan->n_tiles_window), t->cfg.num_heads,
                                 3 * h, h, s));
     }
     {
       GemmArgs a{};
-      a.A = w.att; a.lda = h; a.W = static_cast<const __nv_bfloat16*>(L.proj_w.ptr); a.ldw = h;
+      a.A = w.att; a.A_lo = w.att_lo; a.lda = h; a.W = static_cast<const __nv_bfloat16*>(L.proj_w.ptr); a.ldw = h;
       a.M = static_cast<int>(N); a.N = h; a.K = h;
       a.epilogue = EPI_RESID; a.flags = GEMM_ADD_RESID;
       a.bias = static_cast<const float*>(L.proj_b.ptr);
-      a.x = w.x; a.ldx = h; a.out_bf16 = w.xb; a.ld_out = h;
+      a.x = w.x; a.ldx = h; a.out_bf16 = w.xb; a.out_lo = w.xb_lo; a.ld_out = h;
       a.norm_w = static_cast<const float*>(L.norm2_w.ptr);
       a.ssq = w.ssq;
       if ((rc = G(a, VR2_K_PROJ, "proj")) != VR2_OK) return rc;
     }
     {
       GemmArgs a{};
-      a.A = w.xb; a.lda = h; a.W = static_cast<const __nv_bfloat16*>(L.gu_w.ptr); a.ldw = h;
+      a.A = w.xb; a.A_lo = w.xb_lo; a.lda = h; a.W = static_cast<const __nv_bfloat16*>(L.gu_w.ptr); a.ldw = h;
       a.M = static_cast<int>(N); a.N = 2 * t->ipad; a.K = h;
       a.epilogue = EPI_SWIGLU;
       a.bias = static_cast<const float*>(L.gu_b.ptr);
-      a.out_bf16 = w.hbuf; a.ld_out = t->ipad;
+      a.out_bf16 = w.hbuf; a.out_lo = w.hbuf_lo; a.ld_out = t->ipad;
       a.ssq_in = w.ssq; a.ssq_parts = parts; a.inv_dim = 1.0f / h; a.eps = eps;
       if ((rc = G(a, VR2_K_GATE_UP, "gate_up")) != VR2_OK) return rc;
     }
     {
       GemmArgs a{};
-      a.A = w.hbuf; a.lda = t->ipad; a.W = static_cast<const __nv_bfloat16*>(L.down_w.ptr); a.ldw = t->ipad;
+      a.A = w.hbuf; a.A_lo = w.hbuf_lo; a.lda = t->ipad; a.W = static_cast<const __nv_bfloat16*>(L.down_w.ptr); a.ldw = t->ipad;
       a.M = static_cast<int>(N); a.N = h; a.K = t->ipad;
       a.epilogue = EPI_RESID; a.flags = GEMM_ADD_RESID;
       a.bias = static_cast<const float*>(L.down_b.ptr);
-      a.x = w.x; a.ldx = h; a.out_bf16 = w.xb; a.ld_out = h;
+      a.x = w.x; a.ldx = h; a.out_bf16 = w.xb; a.out_lo = w.xb_lo; a.ld_out = h;
       a.norm_w = static_cast<const float*>(l + 1 < t->cfg.depth ? t->layers[l + 1].norm1_w.ptr : t->lnq_w.ptr);
       a.ssq = w.ssq;
       if ((rc = G(a, VR2_K_DOWN, "down")) != VR2_OK) return rc;
@@ -435,20 +452,20 @@ extern "C" int vr2_tower_forward(vr2_tower* t, const vr2_plan* plan, const void*
   const int md = t->merge_dim;
   {
     ProfScope prof(t, VR2_K_MERGER_NORM, s);
-    VR2_CUDA(rmsnorm_to_bf16(w.x, static_cast<const float*>(t->lnq_w.ptr), w.qkv, N, h, eps, s));
+    VR2_CUDA(rmsnorm_to_bf16(w.x, static_cast<const float*>(t->lnq_w.ptr), w.qkv, w.qkv_lo, N, h, eps, s));
   }
   {
     GemmArgs a{};
-    a.A = w.qkv; a.lda = md; a.W = static_cast<const __nv_bfloat16*>(t->fc1_w.ptr); a.ldw = md;
+    a.A = w.qkv; a.A_lo = w.qkv_lo; a.lda = md; a.W = static_cast<const __nv_bfloat16*>(t->fc1_w.ptr); a.ldw = md;
     a.M = static_cast<int>(T); a.N = md; a.K = md;
     a.epilogue = EPI_STORE; a.flags = GEMM_GELU;
     a.bias = static_cast<const float*>(t->fc1_b.ptr);
-    a.out_bf16 = w.hbuf; a.ld_out = md;
+    a.out_bf16 = w.hbuf; a.out_lo = w.hbuf_lo; a.ld_out = md;
     if ((rc = G(a, VR2_K_FC1, "merger.fc1")) != VR2_OK) return rc;
   }
   {
     GemmArgs a{};
-    a.A = w.hbuf; a.lda = md; a.W = static_cast<const __nv_bfloat16*>(t->fc2_w.ptr); a.ldw = md;
+    a.A = w.hbuf; a.A_lo = w.hbuf_lo; a.lda = md; a.W = static_cast<const __nv_bfloat16*>(t->fc2_w.ptr); a.ldw = md;
     a.M = static_cast<int>(T); a.N = t->cfg.out_hidden_size; a.K = md;
     a.epilogue = EPI_STORE; a.flags = out_dtype == VR2_F32 ? GEMM_OUT_F32 : 0;
     a.bias = static_cast<const float*>(t->fc2_b.ptr);
@@ -459,6 +476,16 @@ extern "C" int vr2_tower_forward(vr2_tower* t, const vr2_plan* plan, const void*
   }
   return VR2_OK;
 }
+
+extern "C" int vr2_tower_set_precision(vr2_tower* t, int32_t precision) {
+  if (t == nullptr) return fail(VR2_ERR_ARG, "vr2_tower_set_precision: null tower");
+  if (precision != VR2_PRECISION_BF16 && precision != VR2_PRECISION_SPLIT)
+    return fail(VR2_ERR_ARG, "vr2_tower_set_precision: unknown precision %d", precision);
+  t->precision = precision;
+  return VR2_OK;
+}
+
+extern "C" int32_t vr2_tower_get_precision(const vr2_tower* t) { return t == nullptr ? -1 : t->precision; }
 
 extern "C" int vr2_tower_profile(vr2_tower* t, uint32_t kind_mask) {
   if (t == nullptr) return fail(VR2_ERR_ARG, "vr2_tower_profile: null tower");
@@ -483,8 +510,23 @@ extern "C" int vr2_tower_profile_read(vr2_tower* t, double* ms_by_kind, int64_t*
 }
 
 // ----------------------------------------------------------------- single operators (test surface)
+static int op_linear_impl(const void* a_dev, const void* a_lo_dev, const void* w_dev, const float* bias, void* out,
+                          int32_t out_dtype, int32_t M, int32_t N, int32_t K, int32_t gelu, void* stream_v);
+
 extern "C" int vr2_op_linear(const void* a_dev, const void* w_dev, const float* bias, void* out, int32_t out_dtype,
                              int32_t M, int32_t N, int32_t K, int32_t gelu, void* stream_v) {
+  return op_linear_impl(a_dev, nullptr, w_dev, bias, out, out_dtype, M, N, K, gelu, stream_v);
+}
+
+extern "C" int vr2_op_linear_split(const void* a_hi_dev, const void* a_lo_dev, const void* w_dev, const float* bias,
+                                   void* out, int32_t out_dtype, int32_t M, int32_t N, int32_t K, int32_t gelu,
+                                   void* stream_v) {
+  if (a_lo_dev == nullptr) return fail(VR2_ERR_ARG, "vr2_op_linear_split: null a_lo");
+  return op_linear_impl(a_hi_dev, a_lo_dev, w_dev, bias, out, out_dtype, M, N, K, gelu, stream_v);
+}
+
+static int op_linear_impl(const void* a_dev, const void* a_lo_dev, const void* w_dev, const float* bias, void* out,
+                          int32_t out_dtype, int32_t M, int32_t N, int32_t K, int32_t gelu, void* stream_v) {
   if (a_dev == nullptr || w_dev == nullptr || out == nullptr) return fail(VR2_ERR_ARG, "vr2_op_linear: null pointer");
   if (out_dtype != VR2_F32 && out_dtype != VR2_BF16) return fail(VR2_ERR_ARG, "vr2_op_linear: out dtype");
   if (K % 8 != 0) return fail(VR2_ERR_ARG, "vr2_op_linear: K %% 8 != 0 (rows must be 16-byte aligned)");
@@ -493,6 +535,7 @@ extern "C" int vr2_op_linear(const void* a_dev, const void* w_dev, const float* 
   VR2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   GemmArgs a{};
   a.A = static_cast<const __nv_bfloat16*>(a_dev); a.lda = K;
+  a.A_lo = static_cast<const __nv_bfloat16*>(a_lo_dev);
   a.W = static_cast<const __nv_bfloat16*>(w_dev); a.ldw = K;
   a.M = M; a.N = N; a.K = K;
   a.epilogue = EPI_STORE;
@@ -509,12 +552,26 @@ extern "C" int vr2_op_rmsnorm(const float* x, const float* w, void* out, int64_t
                               void* stream_v) {
   if (x == nullptr || w == nullptr || out == nullptr) return fail(VR2_ERR_ARG, "vr2_op_rmsnorm: null pointer");
   if (dim % 4 != 0) return fail(VR2_ERR_ARG, "vr2_op_rmsnorm: dim %% 4 != 0");
-  VR2_CUDA(rmsnorm_to_bf16(x, w, static_cast<__nv_bfloat16*>(out), rows, dim, eps, as_stream(stream_v)));
+  VR2_CUDA(rmsnorm_to_bf16(x, w, static_cast<__nv_bfloat16*>(out), nullptr, rows, dim, eps, as_stream(stream_v)));
   return VR2_OK;
 }
 
+static int op_attention_impl(const void* qkv, const void* qkv_lo, void* out, void* out_lo, const int32_t* cu,
+                             int32_t n_seq, int32_t num_heads, void* stream_v);
+
 extern "C" int vr2_op_attention(const void* qkv, void* out, const int32_t* cu, int32_t n_seq, int32_t num_heads,
                                 void* stream_v) {
+  return op_attention_impl(qkv, nullptr, out, nullptr, cu, n_seq, num_heads, stream_v);
+}
+
+extern "C" int vr2_op_attention_split(const void* qkv_hi, const void* qkv_lo, void* out_hi, void* out_lo,
+                                      const int32_t* cu, int32_t n_seq, int32_t num_heads, void* stream_v) {
+  if (qkv_lo == nullptr || out_lo == nullptr) return fail(VR2_ERR_ARG, "vr2_op_attention_split: null lo pointer");
+  return op_attention_impl(qkv_hi, qkv_lo, out_hi, out_lo, cu, n_seq, num_heads, stream_v);
+}
+
+static int op_attention_impl(const void* qkv, const void* qkv_lo, void* out, void* out_lo, const int32_t* cu,
+                             int32_t n_seq, int32_t num_heads, void* stream_v) {
   if (qkv == nullptr || out == nullptr || cu == nullptr || n_seq <= 0) return fail(VR2_ERR_ARG, "vr2_op_attention: null pointer");
   std::vector<int4> tiles;
   for (int i = 0; i < n_seq; ++i) {
@@ -528,7 +585,8 @@ extern "C" int vr2_op_attention(const void* qkv, void* out, const int32_t* cu, i
   VR2_CUDA(cudaMalloc(&d, tiles.size() * 16));
   cudaError_t e = cudaMemcpyAsync(d, tiles.data(), tiles.size() * 16, cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess)
-    e = attention_launch(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out), d,
+    e = attention_launch(static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(qkv_lo),
+                         static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(out_lo), d,
                          static_cast<int>(tiles.size()), num_heads, 3 * num_heads * 80, num_heads * 80, s);
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   cudaFree(d);

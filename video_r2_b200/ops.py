@@ -13,18 +13,33 @@ def _s(t):
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
-def linear(a: torch.Tensor, w: torch.Tensor, bias=None, gelu: bool = False, out_dtype=torch.float32) -> torch.Tensor:
-    """a [M,K] bf16, w [N,K] bf16 -> act(a @ w.T + bias), tcgen05 GEMM with fp32 accumulation."""
+def split_bf16(x: torch.Tensor):
+    """fp32 -> (hi, lo) bf16 with hi = bf16(x), lo = bf16(x - hi): the operand format of the "split" precision."""
+    hi = x.to(torch.bfloat16)
+    lo = (x.float() - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
+def linear(a: torch.Tensor, w: torch.Tensor, bias=None, gelu: bool = False, out_dtype=torch.float32,
+           a_lo: torch.Tensor = None) -> torch.Tensor:
+    """a [M,K] bf16, w [N,K] bf16 -> act((a [+ a_lo]) @ w.T + bias), tcgen05 GEMM with fp32 accumulation."""
     assert a.is_cuda and a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
     a, w = a.contiguous(), w.contiguous()
     M, K = a.shape
     N = w.shape[0]
     out = torch.empty((M, N), dtype=out_dtype, device=a.device)
     b = bias.to(torch.float32).contiguous() if bias is not None else None
+    bp = b.data_ptr() if b is not None else None
+    od = VR2_F32 if out_dtype == torch.float32 else VR2_BF16
     with torch.cuda.device(a.device):
-        check(lib().vr2_op_linear(a.data_ptr(), w.data_ptr(), b.data_ptr() if b is not None else None, out.data_ptr(),
-                                  VR2_F32 if out_dtype == torch.float32 else VR2_BF16, M, N, K, int(gelu), _s(a)),
-              "vr2_op_linear")
+        if a_lo is None:
+            check(lib().vr2_op_linear(a.data_ptr(), w.data_ptr(), bp, out.data_ptr(), od, M, N, K, int(gelu), _s(a)),
+                  "vr2_op_linear")
+        else:
+            assert a_lo.dtype == torch.bfloat16 and a_lo.shape == a.shape
+            a_lo = a_lo.contiguous()
+            check(lib().vr2_op_linear_split(a.data_ptr(), a_lo.data_ptr(), w.data_ptr(), bp, out.data_ptr(), od, M, N,
+                                            K, int(gelu), _s(a)), "vr2_op_linear_split")
     return out
 
 
@@ -39,14 +54,22 @@ def rmsnorm(x: torch.Tensor, w: torch.Tensor, eps: float = 1e-6) -> torch.Tensor
     return out
 
 
-def attention(qkv: torch.Tensor, cu_seqlens, num_heads: int) -> torch.Tensor:
-    """qkv bf16 [N, 3*heads*80] (q | k | v), cu_seqlens int list/tensor -> bf16 [N, heads*80]."""
+def attention(qkv: torch.Tensor, cu_seqlens, num_heads: int, qkv_lo: torch.Tensor = None):
+    """qkv bf16 [N, 3*heads*80] (q | k | v), cu_seqlens int list/tensor -> bf16 [N, heads*80].
+    With qkv_lo (the rounding residual of qkv) runs the split kernel and returns (out_hi, out_lo)."""
     assert qkv.is_cuda and qkv.dtype == torch.bfloat16
     qkv = qkv.contiguous()
     cu = [int(v) for v in (cu_seqlens.tolist() if isinstance(cu_seqlens, torch.Tensor) else cu_seqlens)]
     arr = (C.c_int32 * len(cu))(*cu)
     out = torch.empty((qkv.shape[0], num_heads * 80), dtype=torch.bfloat16, device=qkv.device)
     with torch.cuda.device(qkv.device):
-        check(lib().vr2_op_attention(qkv.data_ptr(), out.data_ptr(), arr, len(cu) - 1, num_heads, _s(qkv)),
-              "vr2_op_attention")
-    return out
+        if qkv_lo is None:
+            check(lib().vr2_op_attention(qkv.data_ptr(), out.data_ptr(), arr, len(cu) - 1, num_heads, _s(qkv)),
+                  "vr2_op_attention")
+            return out
+        assert qkv_lo.dtype == torch.bfloat16 and qkv_lo.shape == qkv.shape
+        qkv_lo = qkv_lo.contiguous()
+        out_lo = torch.empty_like(out)
+        check(lib().vr2_op_attention_split(qkv.data_ptr(), qkv_lo.data_ptr(), out.data_ptr(), out_lo.data_ptr(), arr,
+                                           len(cu) - 1, num_heads, _s(qkv)), "vr2_op_attention_split")
+    return out, out_lo

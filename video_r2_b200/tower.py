@@ -11,6 +11,7 @@ from __future__ import annotations
 import collections
 import ctypes as C
 import dataclasses
+import os
 
 import torch
 
@@ -151,7 +152,10 @@ class VisionTower:
     state_dict: name -> tensor with the HF vision-module names
     ("patch_embed.proj.weight", "blocks.0.attn.qkv.weight", ...), fp32 or bf16, any device."""
 
-    def __init__(self, cfg: VisionConfig, state_dict, device="cuda:0", plan_cache: int = 16):
+    def __init__(self, cfg: VisionConfig, state_dict, device="cuda:0", plan_cache: int = 16, precision=None):
+        """precision: "bf16" (default; activations rounded to bf16 once per GEMM input, as HF's bf16 path)
+        or "split" (hi + lo bf16 operands, ~16 mantissa bits, 2x the MMA work — the mode that meets
+        max-abs 2e-2 against the fp32 reference).  Default comes from $VR2_PRECISION."""
         self.cfg = cfg
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -175,7 +179,15 @@ class VisionTower:
         self._plans = collections.OrderedDict()
         self._plan_cache = plan_cache
         self._ws = None
+        self.set_precision(precision or os.environ.get("VR2_PRECISION", "bf16"))
         self.load_state_dict(state_dict)
+
+    def set_precision(self, precision: str):
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}, got {precision!r}")
+        check(lib().vr2_tower_set_precision(self._h, _lib.PRECISIONS[precision]), "vr2_tower_set_precision")
+        self.precision = precision
+        self._ws = None
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
