@@ -44,7 +44,7 @@ struct Cfg {
   static constexpr int groups = BN == 240 ? 3 : 4;        // epilogue column groups
   static constexpr int epi_warps = 4 * groups;
   static constexpr int threads = (epi_warps + 2) * 32;
-  static constexpr int group_cols = BN / groups;           // 64 (BN=256) or 80 (BN=240)
+  static constexpr int group_cols = BN / groups;           // 64 (BN=256), 80 (BN=240: one head) or 40 (BN=160)
   static constexpr int a_half = BM * BK * 2;               // one A tile (hi or lo)
   static constexpr int a_bytes = a_half * (SPLIT ? 2 : 1);
   static constexpr int b_bytes = BN * BK * 2;
@@ -92,6 +92,31 @@ struct Stage {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (row < rows_valid && chunk * 4 < width) v = __ldg(reinterpret_cast<const float4*>(g + row * ld + chunk * 4));
       *f4(row, chunk) = v;
+    }
+  }
+  // The same [32 x width] fp32 piece, split so the global loads can be issued one chunk ahead of their use:
+  // fetch() -> registers (coalesced: 8 rows x 64 B per instruction), put() -> staging.
+  static __device__ __forceinline__ void fetch_f32(float4 (&pre)[4], const float* g, int64_t ld, int rows_valid, int lane,
+                                                   int width) {
+    const int chunk = lane & 3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int row = (lane >> 2) + 8 * k;
+      pre[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < rows_valid && chunk * 4 < width) pre[k] = *reinterpret_cast<const float4*>(g + row * ld + chunk * 4);
+    }
+  }
+  __device__ __forceinline__ void put_f32(const float4 (&pre)[4], int lane) const {
+    const int chunk = lane & 3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) *f4((lane >> 2) + 8 * k, chunk) = pre[k];
+  }
+  __device__ __forceinline__ void store_f32_w(float* g, int64_t ld, int rows_valid, int lane, int width) const {
+    const int chunk = lane & 3;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int row = (lane >> 2) + 8 * k;
+      if (row < rows_valid && chunk * 4 < width) *reinterpret_cast<float4*>(g + row * ld + chunk * 4) = *f4(row, chunk);
     }
   }
   __device__ __forceinline__ void store_f32(float* g, int64_t ld, int rows_valid, int lane) const {
@@ -291,8 +316,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int n0 = n_blk * BN;
       const uint32_t as = local & 1u;
       const uint32_t use = local >> 1;
-      mbar_wait(&acc_full[as], use & 1u);
-      tc_fence_after();
+      if constexpr (EPI != EPI_RESID && EPI != EPI_QKV) {   // those two start their global loads first
+        mbar_wait(&acc_full[as], use & 1u);
+        tc_fence_after();
+      }
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * kAccStride;
       const int row0 = m0 + quarter * 32;    // first row of this warp
       const int r = row0 + lane;
@@ -350,38 +377,58 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       } else if constexpr (EPI == EPI_RESID) {
+        // (the accumulator wait for this variant happens inside, after the first residual piece is in flight)
         const bool direct = p.row_map != nullptr;   // patch embed: rows scatter through the window permute
+        const bool resid = (p.flags & GEMM_ADD_RESID) != 0;
         const int64_t dest = valid ? (direct ? p.row_map[r] : r) : 0;
+        const int c_begin = cg * GC, c_end = (cg + 1) * GC;
+        float* xpiece = p.x + static_cast<int64_t>(row0) * p.ldx + n0;   // this warp's rows, tile column 0
+        // The residual read is the long pole of this epilogue (x streams from HBM): the first 16-column piece is
+        // requested before the accumulator is even complete and every later piece one iteration ahead of its use
+        // (ncu r01c: 65 % of the stall samples sat on the LDG -> STS dependency when it was loaded in place).
+        float4 pre[4];
+        if (!direct && resid) Stage::fetch_f32(pre, xpiece + c_begin, p.ldx, rows_valid, lane, min(16, c_end - c_begin));
+        mbar_wait(&acc_full[as], use & 1u);
+        tc_fence_after();
         float ss = 0.f;
 #pragma unroll 1
-        for (int c = cg * GC; c < (cg + 1) * GC; c += 16) {
+        for (int c = c_begin; c < c_end; c += 16) {
+          const int wdt = min(16, c_end - c);     // 16, or 8 for the tail of a 40-column group
           uint32_t v[16];
           tmem_ld16(taddr + c, v);
-          float* xg = p.x + static_cast<int64_t>(row0) * p.ldx + n0 + c;          // piece origin (identity rows)
-          if (!direct && (p.flags & GEMM_ADD_RESID)) st.load_f32(xg, p.ldx, rows_valid, lane);
+          float* xg = xpiece + c;                  // piece origin (identity rows)
+          if (!direct && resid) {
+            st.put_f32(pre, lane);
+            if (c + 16 < c_end) Stage::fetch_f32(pre, xg + 16, p.ldx, rows_valid, lane, min(16, c_end - c - 16));
+          }
           tmem_ld_wait();
           __syncwarp();
           float f[16];
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
             float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + j));
             float4 xo = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.flags & GEMM_ADD_RESID) {
-              if (direct) { if (valid) xo = *reinterpret_cast<const float4*>(p.x + dest * p.ldx + n0 + c + j); }
-              else xo = *st.f4(lane, j >> 2);
+            float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < wdt) {
+              a4 = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+              if (p.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + j));
+              if (resid) {
+                if (direct) { if (valid) xo = *reinterpret_cast<const float4*>(p.x + dest * p.ldx + n0 + c + j); }
+                else xo = *st.f4(lane, j >> 2);
+              }
             }
-            f[j] = __uint_as_float(v[j]) + b.x + xo.x;
-            f[j + 1] = __uint_as_float(v[j + 1]) + b.y + xo.y;
-            f[j + 2] = __uint_as_float(v[j + 2]) + b.z + xo.z;
-            f[j + 3] = __uint_as_float(v[j + 3]) + b.w + xo.w;
+            f[j] = a4.x + b.x + xo.x;
+            f[j + 1] = a4.y + b.y + xo.y;
+            f[j + 2] = a4.z + b.z + xo.z;
+            f[j + 3] = a4.w + b.w + xo.w;
           }
 #pragma unroll
           for (int j = 0; j < 16; ++j) ss = fmaf(f[j], f[j], ss);
           float xw[16];   // x * w of the RMSNorm that reads x next: the next GEMM's A operand before rounding
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
-            const float4 w = __ldg(reinterpret_cast<const float4*>(p.norm_w + n0 + c + j));
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < wdt) w = __ldg(reinterpret_cast<const float4*>(p.norm_w + n0 + c + j));
             xw[j] = f[j] * w.x;
             xw[j + 1] = f[j + 1] * w.y;
             xw[j + 2] = f[j + 2] * w.z;
@@ -391,89 +438,94 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (valid) {
               float* xr = p.x + dest * p.ldx + n0 + c;
 #pragma unroll
-              for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(xr + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-              emit_row<SPLIT>(xw, p.out_bf16 + dest * p.ld_out + n0 + c, p.out_lo ? p.out_lo + dest * p.ld_out + n0 + c : nullptr);
+              for (int j = 0; j < 16; j += 4)
+                if (j < wdt) *reinterpret_cast<float4*>(xr + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              if (wdt == 16) {
+                emit_row<SPLIT>(xw, p.out_bf16 + dest * p.ld_out + n0 + c, p.out_lo ? p.out_lo + dest * p.ld_out + n0 + c : nullptr);
+              } else {
+                uint32_t hi[8], lo[8];
+                pack16<SPLIT>(xw, hi, lo);
+                *reinterpret_cast<uint4*>(p.out_bf16 + dest * p.ld_out + n0 + c) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                if constexpr (SPLIT) {
+                  if (p.out_lo != nullptr)
+                    *reinterpret_cast<uint4*>(p.out_lo + dest * p.ld_out + n0 + c) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+              }
             }
           } else {
+            __syncwarp();   // every lane has read its residual row before the tile is overwritten
 #pragma unroll
             for (int j = 0; j < 4; ++j) *st.f4(lane, j) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
             __syncwarp();
-            st.store_f32(xg, p.ldx, rows_valid, lane);
+            st.store_f32_w(xg, p.ldx, rows_valid, lane, wdt);
             __syncwarp();
             const int64_t off = static_cast<int64_t>(row0) * p.ld_out + n0 + c;
-            emit_piece<SPLIT>(st, xw, p.out_bf16 + off, p.out_lo + off, p.ld_out, rows_valid, lane, 16);
+            emit_piece<SPLIT>(st, xw, p.out_bf16 + off, p.out_lo + off, p.ld_out, rows_valid, lane, wdt);
           }
         }
-        // one partial per (row, 64-column group): deterministic, no atomics
-        if (valid) p.ssq[dest * (num_n_blocks * C::groups) + n_blk * C::groups + cg] = ss;
+        // one partial per (row, column group), part-major [N/40][M]: deterministic, no atomics, coalesced both ways
+        if (valid) p.ssq[static_cast<int64_t>(n_blk * C::groups + cg) * p.M + dest] = ss;
       } else if constexpr (EPI == EPI_QKV) {
         // Tile = 3 heads of 80, one head per column group; rotary pairs (d, d+40) live in one thread's row.
+        // A head is processed in 5 pieces of 8 pairs.  Everything that does not depend on the accumulator (the
+        // row's sum of squares, the first cos / sin piece) is requested before waiting for it, later cos / sin
+        // pieces one iteration ahead.  One staging pass carries cos (chunks 0-1) and sin (chunks 2-3) of a
+        // piece; one more carries the rotated first halves (columns i0..) and second halves (40 + i0..).
+        const int col0 = n0 + cg * 80;
+        const bool rot = col0 < 2 * (p.N / 3);  // q and k heads rotate, v heads do not
+        const int chunk = lane & 3;
+        const float* tab = (chunk < 2 ? p.cos_tab : p.sin_tab) + static_cast<int64_t>(row0) * 40 + (chunk & 1) * 4;
+        auto fetch_cs = [&](float4 (&pre)[4], int i0) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int row = (lane >> 2) + 8 * k;
+            pre[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < rows_valid) pre[k] = __ldg(reinterpret_cast<const float4*>(tab + row * 40 + i0));
+          }
+        };
+        float4 pre[4];
+        if (rot) fetch_cs(pre, 0);
         float rstd = 0.f;
         if (valid) {
           float s = 0.f;
-          const float* sp = p.ssq_in + static_cast<int64_t>(r) * p.ssq_parts;
-          for (int q = 0; q < p.ssq_parts; q += 4) {
-            const float4 t4 = *reinterpret_cast<const float4*>(sp + q);
-            s += (t4.x + t4.y) + (t4.z + t4.w);
-          }
+          for (int q = 0; q < p.ssq_parts; ++q) s += p.ssq_in[static_cast<int64_t>(q) * p.M + r];
           rstd = rsqrtf(s * p.inv_dim + p.eps);
         }
-        const int col0 = n0 + cg * 80;
-        const bool rot = col0 < 2 * (p.N / 3);  // q and k heads rotate, v heads do not
-        __nv_bfloat16* og = p.out_bf16 + static_cast<int64_t>(row0) * p.ld_out + col0;   // head origin, this warp's rows
+        mbar_wait(&acc_full[as], use & 1u);
+        tc_fence_after();
+        const int64_t og = static_cast<int64_t>(row0) * p.ld_out + col0;   // head origin, this warp's rows
 #pragma unroll 1
-        for (int i0 = 0; i0 < 40; i0 += 16) {
-          const int wdt = (40 - i0) < 16 ? 8 : 16;   // 16, 16, 8 pairs
-          uint32_t lo[16], hi[16];
+        for (int i0 = 0; i0 < 40; i0 += 8) {
+          uint32_t lo[8], hi[8];
           tmem_ld8(taddr + cg * 80 + i0, lo);
           tmem_ld8(taddr + cg * 80 + 40 + i0, hi);
-          if (wdt == 16) {
-            tmem_ld8(taddr + cg * 80 + i0 + 8, lo + 8);
-            tmem_ld8(taddr + cg * 80 + 40 + i0 + 8, hi + 8);
-          }
-          float cs[16], sn[16];
+          float4 c0, c1, s0, s1;
           if (rot) {
-            // cos / sin rows of this warp's 32 patches, pulled through the staging buffer row-contiguously
-            st.load_f32_w(p.cos_tab + static_cast<int64_t>(row0) * 40 + i0, 40, rows_valid, lane, wdt);
+            st.put_f32(pre, lane);
             __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 t4 = *st.f4(lane, j);
-              cs[4 * j] = t4.x; cs[4 * j + 1] = t4.y; cs[4 * j + 2] = t4.z; cs[4 * j + 3] = t4.w;
-            }
+            c0 = *st.f4(lane, 0); c1 = *st.f4(lane, 1); s0 = *st.f4(lane, 2); s1 = *st.f4(lane, 3);
             __syncwarp();
-            st.load_f32_w(p.sin_tab + static_cast<int64_t>(row0) * 40 + i0, 40, rows_valid, lane, wdt);
-            __syncwarp();
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 t4 = *st.f4(lane, j);
-              sn[4 * j] = t4.x; sn[4 * j + 1] = t4.y; sn[4 * j + 2] = t4.z; sn[4 * j + 3] = t4.w;
-            }
-            __syncwarp();
+            if (i0 + 8 < 40) fetch_cs(pre, i0 + 8);   // flies while this piece is rotated, packed and stored
           }
+          const float4 ba0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i0));
+          const float4 ba1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i0 + 4));
+          const float4 bb0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 40 + i0));
+          const float4 bb1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 40 + i0 + 4));
           tmem_ld_wait();
-          float a[16], b[16];
-#pragma unroll
-          for (int q = 0; q < 16; q += 4) {
-            if (q < wdt) {
-              const float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i0 + q));
-              const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 40 + i0 + q));
-              a[q] = fmaf(__uint_as_float(lo[q]), rstd, ba.x);
-              a[q + 1] = fmaf(__uint_as_float(lo[q + 1]), rstd, ba.y);
-              a[q + 2] = fmaf(__uint_as_float(lo[q + 2]), rstd, ba.z);
-              a[q + 3] = fmaf(__uint_as_float(lo[q + 3]), rstd, ba.w);
-              b[q] = fmaf(__uint_as_float(hi[q]), rstd, bb.x);
-              b[q + 1] = fmaf(__uint_as_float(hi[q + 1]), rstd, bb.y);
-              b[q + 2] = fmaf(__uint_as_float(hi[q + 2]), rstd, bb.z);
-              b[q + 3] = fmaf(__uint_as_float(hi[q + 3]), rstd, bb.w);
-            } else {
-              a[q] = a[q + 1] = a[q + 2] = a[q + 3] = 0.f;
-              b[q] = b[q + 1] = b[q + 2] = b[q + 3] = 0.f;
-            }
-          }
+          float a[8], b[8];
+          a[0] = fmaf(__uint_as_float(lo[0]), rstd, ba0.x); a[1] = fmaf(__uint_as_float(lo[1]), rstd, ba0.y);
+          a[2] = fmaf(__uint_as_float(lo[2]), rstd, ba0.z); a[3] = fmaf(__uint_as_float(lo[3]), rstd, ba0.w);
+          a[4] = fmaf(__uint_as_float(lo[4]), rstd, ba1.x); a[5] = fmaf(__uint_as_float(lo[5]), rstd, ba1.y);
+          a[6] = fmaf(__uint_as_float(lo[6]), rstd, ba1.z); a[7] = fmaf(__uint_as_float(lo[7]), rstd, ba1.w);
+          b[0] = fmaf(__uint_as_float(hi[0]), rstd, bb0.x); b[1] = fmaf(__uint_as_float(hi[1]), rstd, bb0.y);
+          b[2] = fmaf(__uint_as_float(hi[2]), rstd, bb0.z); b[3] = fmaf(__uint_as_float(hi[3]), rstd, bb0.w);
+          b[4] = fmaf(__uint_as_float(hi[4]), rstd, bb1.x); b[5] = fmaf(__uint_as_float(hi[5]), rstd, bb1.y);
+          b[6] = fmaf(__uint_as_float(hi[6]), rstd, bb1.z); b[7] = fmaf(__uint_as_float(hi[7]), rstd, bb1.w);
           if (rot) {
+            const float cs[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+            const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
+            for (int q = 0; q < 8; ++q) {
               // q*cos + rotate_half(q)*sin in fp32 (HF :161-166)
               const float na = a[q] * cs[q] - b[q] * sn[q];
               const float nb = b[q] * cs[q] + a[q] * sn[q];
@@ -481,21 +533,47 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               b[q] = nb;
             }
           }
-          // first half -> columns [i0, i0+wdt), second half -> [40+i0, 40+i0+wdt)
-          __nv_bfloat16* og_lo = p.out_lo + static_cast<int64_t>(row0) * p.ld_out + col0;
-          emit_piece<SPLIT>(st, a, og + i0, og_lo + i0, p.ld_out, rows_valid, lane, wdt);
-          emit_piece<SPLIT>(st, b, og + 40 + i0, og_lo + 40 + i0, p.ld_out, rows_valid, lane, wdt);
+          // staging bf16 [32][16]: first halves in columns 0-7 (-> head columns i0..), second halves in 8-15 (-> 40 + i0..)
+          uint32_t ah[4], al[4], bh[4], bl[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if constexpr (SPLIT) {
+              split_bf16x2(a[2 * q], a[2 * q + 1], ah[q], al[q]);
+              split_bf16x2(b[2 * q], b[2 * q + 1], bh[q], bl[q]);
+            } else {
+              ah[q] = pack_bf16x2(a[2 * q], a[2 * q + 1]);
+              bh[q] = pack_bf16x2(b[2 * q], b[2 * q + 1]);
+            }
+          }
+          const int half = lane & 1;
+          const int64_t piece = og + (half ? 40 + i0 : i0);
+          *st.h8(lane, 0) = make_uint4(ah[0], ah[1], ah[2], ah[3]);
+          *st.h8(lane, 1) = make_uint4(bh[0], bh[1], bh[2], bh[3]);
+          __syncwarp();
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const int row = (lane >> 1) + 16 * k;
+            if (row < rows_valid) *reinterpret_cast<uint4*>(p.out_bf16 + piece + row * p.ld_out) = *st.h8(row, half);
+          }
+          __syncwarp();
+          if constexpr (SPLIT) {
+            *st.h8(lane, 0) = make_uint4(al[0], al[1], al[2], al[3]);
+            *st.h8(lane, 1) = make_uint4(bl[0], bl[1], bl[2], bl[3]);
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const int row = (lane >> 1) + 16 * k;
+              if (row < rows_valid) *reinterpret_cast<uint4*>(p.out_lo + piece + row * p.ld_out) = *st.h8(row, half);
+            }
+            __syncwarp();
+          }
         }
       } else if constexpr (EPI == EPI_SWIGLU) {
         // Tile columns [0,128) are gate rows, [128,256) the matching up rows; group cg owns 32 outputs.
         float rstd = 0.f;
         if (valid) {
           float s = 0.f;
-          const float* sp = p.ssq_in + static_cast<int64_t>(r) * p.ssq_parts;
-          for (int q = 0; q < p.ssq_parts; q += 4) {
-            const float4 t4 = *reinterpret_cast<const float4*>(sp + q);
-            s += (t4.x + t4.y) + (t4.z + t4.w);
-          }
+          for (int q = 0; q < p.ssq_parts; ++q) s += p.ssq_in[static_cast<int64_t>(q) * p.M + r];
           rstd = rsqrtf(s * p.inv_dim + p.eps);
         }
         constexpr int OC = BN / 2 / C::groups;  // 32 output columns per group
@@ -579,19 +657,28 @@ cudaError_t launch_any(const GemmArgs& a, int num_sms, cudaStream_t stream, cons
 
 }  // namespace
 
-bool tma_encode_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
-                        uint32_t box_inner, uint32_t box_rows) {
+bool tma_encode_2d(CUtensorMap* map, int dtype, int elem_bytes, const void* base, uint64_t inner, uint64_t rows,
+                   uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_rows, bool swizzle128) {
   EncodeFn fn = resolve_encode();
   if (fn == nullptr) return false;
+  (void)elem_bytes;
   const cuuint64_t dims[2] = {inner, rows};
   const cuuint64_t strides[1] = {row_stride_bytes};
   const cuuint32_t box[2] = {box_inner, box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = fn(map, static_cast<CUtensorMapDataType>(dtype), 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
+
+bool tma_encode_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
+                        uint32_t box_inner, uint32_t box_rows) {
+  return tma_encode_2d(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, inner, rows, row_stride_bytes, box_inner, box_rows,
+                       true);
+}
+
+int gemm_resid_parts(const GemmArgs& a) { return gemm2_supports(a) ? gemm2_resid_parts(a.N) : a.N / 40; }
 
 cudaError_t gemm_launch(const GemmArgs& a, int num_sms, cudaStream_t stream, const char** err) {
   static const char* none = "";
@@ -604,6 +691,28 @@ cudaError_t gemm_launch(const GemmArgs& a, int num_sms, cudaStream_t stream, con
       (reinterpret_cast<uintptr_t>(a.W) & 15)) {
     *err = "gemm: operand rows must be 16-byte aligned for TMA";
     return cudaErrorInvalidValue;
+  }
+  if (gemm2_supports(a)) {
+    switch (a.epilogue) {
+      case EPI_QKV:
+        if (a.bias == nullptr || a.ssq_in == nullptr || a.cos_tab == nullptr || a.sin_tab == nullptr || a.out_bf16 == nullptr) {
+          *err = "gemm: EPI_QKV needs bias/ssq/cos/sin/out";
+          return cudaErrorInvalidValue;
+        }
+        break;
+      case EPI_RESID:
+        if (a.x == nullptr || a.out_bf16 == nullptr || a.norm_w == nullptr || a.ssq == nullptr) {
+          *err = "gemm: EPI_RESID needs x/xb/norm_w/ssq";
+          return cudaErrorInvalidValue;
+        }
+        break;
+      default:
+        if (a.bias == nullptr || a.ssq_in == nullptr || a.out_bf16 == nullptr) {
+          *err = "gemm: EPI_SWIGLU needs bias/ssq/out";
+          return cudaErrorInvalidValue;
+        }
+    }
+    return gemm2_launch(a, num_sms, stream, err);
   }
   if (a.A_lo != nullptr) {
     if (reinterpret_cast<uintptr_t>(a.A_lo) & 15) {
@@ -627,20 +736,22 @@ cudaError_t gemm_launch(const GemmArgs& a, int num_sms, cudaStream_t stream, con
       }
       return launch_any<256, EPI_STORE>(a, num_sms, stream, err);
     case EPI_RESID:
-      if (a.N % 256 != 0 || a.x == nullptr || a.out_bf16 == nullptr || a.norm_w == nullptr || a.ssq == nullptr) {
-        *err = "gemm: EPI_RESID needs N % 256 == 0 and x/xb/norm_w/ssq";
+      if (a.N % 160 != 0 || a.x == nullptr || a.out_bf16 == nullptr || a.norm_w == nullptr || a.ssq == nullptr) {
+        *err = "gemm: EPI_RESID needs N % 160 == 0 and x/xb/norm_w/ssq";
         return cudaErrorInvalidValue;
       }
-      return launch_any<256, EPI_RESID>(a, num_sms, stream, err);
+      // 128 x 160 tiles: N = 1280 gives 8 column blocks, so M = 16384 is 1024 tiles = 6.92 waves of 148 CTAs
+      // (128 x 256 tiles: 640 tiles = 4.32 waves, 13.5 % of the last wave idle)
+      return launch_any<160, EPI_RESID>(a, num_sms, stream, err);
     case EPI_QKV:
-      if (a.N % 240 != 0 || a.ssq_parts % 4 != 0 || a.bias == nullptr || a.ssq_in == nullptr || a.cos_tab == nullptr ||
+      if (a.N % 240 != 0 || a.bias == nullptr || a.ssq_in == nullptr || a.cos_tab == nullptr ||
           a.sin_tab == nullptr || a.out_bf16 == nullptr) {
         *err = "gemm: EPI_QKV needs N % 240 == 0 and bias/ssq/cos/sin/out";
         return cudaErrorInvalidValue;
       }
       return launch_any<240, EPI_QKV>(a, num_sms, stream, err);
     case EPI_SWIGLU:
-      if (a.N % 256 != 0 || a.ssq_parts % 4 != 0 || a.bias == nullptr || a.ssq_in == nullptr || a.out_bf16 == nullptr) {
+      if (a.N % 256 != 0 || a.bias == nullptr || a.ssq_in == nullptr || a.out_bf16 == nullptr) {
         *err = "gemm: EPI_SWIGLU needs N % 256 == 0 and bias/ssq/out";
         return cudaErrorInvalidValue;
       }

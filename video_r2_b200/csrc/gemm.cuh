@@ -42,8 +42,8 @@ struct GemmArgs {
   int64_t ld_out;
   const int* row_map;      // destination row of source row r (null = identity)
   const float* norm_w;     // EPI_RESID: weight of the RMSNorm that reads x next, [N]
-  float* ssq;              // partial sum of squares: written [rows, N/64] by EPI_RESID (one per 64-column group)
-  const float* ssq_in;     // read by EPI_QKV / EPI_SWIGLU, [M, ssq_parts]
+  float* ssq;              // partial sum of squares: written part-major [parts][M] by EPI_RESID (parts = gemm_resid_parts())
+  const float* ssq_in;     // read by EPI_QKV / EPI_SWIGLU, [ssq_parts][M]
   int ssq_parts;
   float inv_dim;           // 1 / hidden
   float eps;
@@ -54,6 +54,19 @@ struct GemmArgs {
 // Enqueues the GEMM on `stream`.  Returns cudaSuccess or the launch error; shape
 // violations set *err_msg (static string) and return cudaErrorInvalidValue.
 cudaError_t gemm_launch(const GemmArgs& args, int num_sms, cudaStream_t stream, const char** err_msg);
+
+// Number of sum-of-squares partials per row this EPI_RESID launch writes (depends on the kernel that runs it).
+int gemm_resid_parts(const GemmArgs& args);
+
+// CTA-pair (cta_group::2) kernel for the QKV / residual / gate|up GEMMs (gemm2.cu); gemm_launch() routes to it
+// whenever gemm2_supports().
+bool gemm2_supports(const GemmArgs& args);
+int gemm2_resid_parts(int n);
+cudaError_t gemm2_launch(const GemmArgs& args, int num_sms, cudaStream_t stream, const char** err_msg);
+
+// dtype: a CUtensorMapDataType; swizzle128: SWIZZLE_128B (else none)
+bool tma_encode_2d(CUtensorMap* map, int dtype, int elem_bytes, const void* base, uint64_t inner, uint64_t rows,
+                   uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_rows, bool swizzle128);
 
 // Resolves cuTensorMapEncodeTiled through the runtime (no link against libcuda).
 bool tma_encode_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,

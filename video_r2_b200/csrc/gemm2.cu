@@ -1,0 +1,546 @@
+// CTA-pair (tcgen05 cta_group::2) GEMM for the three GEMM shapes that carry 97 % of the tower's FLOPs:
+//
+//   EPI_QKV     C = xb * Wqkv^T      epilogue: * rstd(x), + bias, 2-D rotary on q,k, bf16           (N = 3840, BN = 240)
+//   EPI_RESID   C = A  * W^T         epilogue: x += C + bias (fp32), xb = bf16(x * w_norm), sum x^2  (N = 1280, BN = 160)
+//   EPI_SWIGLU  C = xb * Wgu^T       epilogue: * rstd, + bias, silu(gate) * up, bf16                 (N = 6912, BN = 256)
+//
+// Why a second kernel (ncu r01c, profiles/): in the single-CTA kernel (gemm.cu) the tensor core's operand reads
+// take 75 % of the SM's L1/shared data pipe at full rate (128 x 256 tile: 48 KB per 512 cycles) and the epilogue's
+// LSU traffic (staging through shared memory, row-strided global accesses) takes the rest: QKV and gate|up sat at
+// 100 % of that pipe with the tensor pipe at 51 % / 77 %.  Here
+//   * two CTAs of a cluster share one 256 x BN tile: each loads its own 128 rows of A and HALF of W's rows, the
+//     leader issues tcgen05.mma.cta_group::2 — operand reads per SM drop to 32 KB per 512 cycles (50 %);
+//   * the stage ring shrinks by a third, which pays for epilogue buffers in shared memory;
+//   * every epilogue input/output moves by TMA: the fp32 residual tile and the cos/sin rows are bulk-loaded while the
+//     MMAs of the tile run, results are written to shared memory once (thread = row, 16-byte stores, layouts chosen
+//     conflict-free: 80-byte rows or 128-byte swizzle) and leave through bulk tensor stores issued by a dedicated
+//     warp, so epilogue warps issue no global loads/stores except the L1-resident bias / norm-weight vectors.
+//
+// Warp roles per CTA: E epilogue warps (4 TMEM lane quarters x column groups), 1 TMA producer, 1 MMA issuer (leader
+// CTA only), 1 store warp (TMA stores, residual / rotary-table loads, sum-of-squares reduction).
+// Replaces the cuBLAS calls behind HF modeling_qwen2_5_vl.py:221-287 (qkv, proj) and :87-88 (gate/up/down).
+#include "gemm.cuh"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "ptx.cuh"
+
+namespace vr2 {
+
+namespace {
+
+constexpr int BM = 128;          // accumulator rows per CTA (256 per pair)
+constexpr int BK = 64;           // one 128-byte swizzle atom of bf16
+constexpr int UK = 16;
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
+constexpr int kBox = 128 * 80;   // one [128 rows x 80 bytes] epilogue box (20 fp32 or 40 bf16 columns)
+
+template <int EPI>
+struct Cfg2;
+
+template <>
+struct Cfg2<EPI_QKV> {
+  static constexpr int BN = 240, groups = 3, stages = 4;
+  static constexpr int out_bytes = 6 * kBox;   // 3 heads x (first | second rotary half) boxes of 40 bf16 columns
+  static constexpr int aux_bytes = 4 * kBox;   // cos: 2 boxes of 20 fp32 columns, sin: 2 boxes
+};
+template <>
+struct Cfg2<EPI_SWIGLU> {
+  static constexpr int BN = 256, groups = 4, stages = 5;
+  static constexpr int out_bytes = 2 * 2 * 16384;  // double-buffered 128 x 128 bf16 as two 128B-swizzled 64-column boxes
+  static constexpr int aux_bytes = 0;
+};
+template <>
+struct Cfg2<EPI_RESID> {
+  static constexpr int BN = 160, groups = 4, stages = 4;
+  static constexpr int out_bytes = 8 * kBox + 4 * kBox;  // fp32 residual tile (in place) + bf16 operand tile
+  static constexpr int aux_bytes = 4 * 128 * 4;          // per column group partial sums of squares
+};
+
+template <int EPI>
+struct Lay {
+  using C = Cfg2<EPI>;
+  static constexpr int BN = C::BN;
+  static constexpr int half_n = BN / 2;
+  static constexpr int epi_warps = 4 * C::groups;
+  static constexpr int threads = (epi_warps + 3) * 32;
+  static constexpr int a_bytes = BM * BK * 2;
+  static constexpr int b_bytes = half_n * BK * 2;
+  static constexpr int stage_bytes = a_bytes + b_bytes;
+  static constexpr int ring_bytes = C::stages * stage_bytes;
+  static constexpr int out_off = ring_bytes;
+  static constexpr int aux_off = out_off + C::out_bytes;
+  static constexpr int bar_off = aux_off + C::aux_bytes;
+  static constexpr int smem_bytes = bar_off + 512;
+  static_assert(stage_bytes % 1024 == 0 && a_bytes % 1024 == 0, "SWIZZLE_128B tiles need 1024-byte alignment");
+  static_assert(smem_bytes <= 232448, "exceeds the 227 KB shared-memory limit");
+};
+
+__device__ __forceinline__ float silu(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Lay<EPI>::threads, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
+             const __grid_constant__ CUtensorMap tm2, const GemmArgs p) {
+  using L = Lay<EPI>;
+  using C = Cfg2<EPI>;
+  constexpr int BN = L::BN;
+  constexpr int E = L::epi_warps;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // no static shared memory in this kernel: the window starts aligned
+
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::bar_off);
+  uint64_t* empty_bar = full_bar + C::stages;
+  uint64_t* acc_full = empty_bar + C::stages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* store_ready = acc_empty + 2;
+  uint64_t* out_free = store_ready + 1;   // [2]
+  uint64_t* aux_full = out_free + 2;      // residual tile / rotary tables landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + 1);
+  uint8_t* out_base = smem + L::out_off;
+  uint8_t* aux_base = smem + L::aux_off;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int num_n = p.N / BN;
+  const int num_pair_m = (p.M + 2 * BM - 1) / (2 * BM);
+  const int num_tiles = num_pair_m * num_n;
+  const int num_k_blocks = (p.K + BK - 1) / BK;
+  // QKV walks a contiguous range of tiles (same rows for up to 16 consecutive tiles: the cos/sin rows are loaded
+  // once per row block); the other two interleave clusters over tiles (n fastest: co-resident clusters share W and
+  // an A band in L2).
+  const int tile_begin = EPI == EPI_QKV ? static_cast<int>(static_cast<int64_t>(cluster_id) * num_tiles / num_clusters) : cluster_id;
+  const int tile_end = EPI == EPI_QKV ? static_cast<int>(static_cast<int64_t>(cluster_id + 1) * num_tiles / num_clusters) : num_tiles;
+  const int tile_step = EPI == EPI_QKV ? 1 : num_clusters;
+
+  constexpr int kProducerWarp = E, kMmaWarp = E + 1, kStoreWarp = E + 2;
+  if (warp == kProducerWarp && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tm0);
+    if constexpr (EPI != EPI_SWIGLU) tma_prefetch_desc(&tm1);
+    if constexpr (EPI == EPI_QKV) tma_prefetch_desc(&tm2);
+    for (int s = 0; s < C::stages; ++s) {
+      mbar_init(&full_bar[s], 1);    // leader's: its own expect_tx arrive; both CTAs' bytes complete on it
+      mbar_init(&empty_bar[s], 1);   // multicast tcgen05.commit arrives once in each CTA
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 2 * E);  // leader's: every epilogue warp of both CTAs
+      mbar_init(&out_free[s], 1);
+    }
+    mbar_init(store_ready, E);
+    mbar_init(aux_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) {
+    tmem_alloc_2cta(tmem_slot, kTmemCols);
+    tmem_relinquish_2cta();
+  }
+  tc_fence_before();
+  cluster_sync_all();   // barrier inits and the TMEM allocation of both CTAs are visible to the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kProducerWarp) {
+    // ------------------------------------------------------------ TMA producer (one lane, both CTAs)
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+        const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
+        const int n0 = (tile % num_n) * BN + static_cast<int>(rank) * L::half_n;
+        for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+          const uint32_t s = it % C::stages;
+          const uint32_t ph = (it / C::stages) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          uint8_t* sa = smem + s * L::stage_bytes;
+          uint8_t* sb = sa + L::a_bytes;
+          const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);   // the leader's barrier tracks the pair
+          if (leader) mbar_expect_tx(&full_bar[s], 2 * L::stage_bytes);
+          tma_load_2d_2cta(sa, &tmA, bar, kb * BK, m0);
+          tma_load_2d_2cta(sb, &tmB, bar, kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ------------------------------------------------------------ MMA issuer (one lane of the leader CTA)
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+      uint32_t it = 0;
+      uint32_t local = 0;
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++local) {
+        const uint32_t as = local & 1u;
+        const uint32_t use = local >> 1;
+        mbar_wait(&acc_empty[as], (use & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * kAccStride;
+        for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+          const uint32_t s = it % C::stages;
+          const uint32_t ph = (it / C::stages) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * L::stage_bytes);
+          const uint32_t b_addr = a_addr + L::a_bytes;
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            const uint64_t da = umma_desc_sw128(a_addr + k * UK * 2);
+            const uint64_t db = umma_desc_sw128(b_addr + k * UK * 2);
+            umma_bf16_2cta(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2cta(&empty_bar[s], 0x3);   // frees this stage in both CTAs
+        }
+        umma_commit_2cta(&acc_full[as], 0x3);     // accumulators of both CTAs complete
+      }
+    }
+  } else if (warp == kStoreWarp) {
+    // ------------------------------------------------------------ store warp: everything the epilogue moves by TMA
+    uint32_t local = 0;
+    if constexpr (EPI == EPI_RESID) {
+      float* red = reinterpret_cast<float*>(aux_base);
+      auto load_x = [&](int tile) {   // residual tile of `tile` -> out_base (8 boxes of 20 fp32 columns)
+        const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
+        const int n0 = (tile % num_n) * BN;
+        mbar_expect_tx(aux_full, 8 * kBox);
+        for (int b = 0; b < 8; ++b) tma_load_2d(out_base + b * kBox, &tm0, aux_full, n0 + b * 20, m0);
+      };
+      if (lane == 0 && tile_begin < tile_end) load_x(tile_begin);
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++local) {
+        const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
+        const int n_blk = tile % num_n;
+        const int n0 = n_blk * BN;
+        mbar_wait(store_ready, local & 1u);
+        if (lane == 0) {
+          for (int b = 0; b < 8; ++b) tma_store_2d(&tm0, out_base + b * kBox, n0 + b * 20, m0);
+          for (int b = 0; b < 4; ++b) tma_store_2d(&tm1, out_base + (8 + b) * kBox, n0 + b * 40, m0);
+          tma_store_commit();
+        }
+        // sum of squares of the new residual rows over this tile's 160 columns: one value per (row, column block),
+        // part-major [N/160][M] so producers and consumers both touch it coalesced; fixed order -> deterministic
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int row = lane + 32 * k;
+          const float s = (red[row] + red[128 + row]) + (red[256 + row] + red[384 + row]);
+          if (m0 + row < p.M) p.ssq[static_cast<int64_t>(n_blk) * p.M + m0 + row] = s;
+        }
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_wait_read<0>();   // the stores have read the tile: the buffers may be refilled
+          if (tile + tile_step < tile_end) load_x(tile + tile_step);
+        }
+      }
+    } else if constexpr (EPI == EPI_QKV) {
+      if (lane == 0) {
+        auto load_cs = [&](int tile) {   // cos / sin rows of this CTA's 128 patches: 2 + 2 boxes of 20 fp32 columns
+          const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
+          mbar_expect_tx(aux_full, 4 * kBox);
+          tma_load_2d(aux_base, &tm1, aux_full, 0, m0);
+          tma_load_2d(aux_base + kBox, &tm1, aux_full, 20, m0);
+          tma_load_2d(aux_base + 2 * kBox, &tm2, aux_full, 0, m0);
+          tma_load_2d(aux_base + 3 * kBox, &tm2, aux_full, 20, m0);
+        };
+        if (tile_begin < tile_end) load_cs(tile_begin);
+        for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++local) {
+          const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
+          const int n0 = (tile % num_n) * BN;
+          mbar_wait(store_ready, local & 1u);
+          // every epilogue warp is done with the tables: fetch the next row block's if the rows change
+          if (tile + 1 < tile_end && (tile + 1) / num_n != tile / num_n) load_cs(tile + 1);
+          for (int b = 0; b < 6; ++b) tma_store_2d(&tm0, out_base + b * kBox, n0 + b * 40, m0);
+          tma_store_commit();
+          tma_store_wait_read<0>();
+          mbar_arrive(&out_free[0]);
+        }
+      }
+    } else {  // EPI_SWIGLU
+      if (lane == 0) {
+        for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++local) {
+          const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
+          const int n_blk = tile % num_n;
+          mbar_wait(store_ready, local & 1u);
+          const uint8_t* ob = out_base + (local & 1u) * 32768;
+          tma_store_2d(&tm0, ob, n_blk * (BN / 2), m0);
+          tma_store_2d(&tm0, ob + 16384, n_blk * (BN / 2) + 64, m0);
+          tma_store_commit();
+          if (local >= 1) {
+            tma_store_wait_read<1>();            // the previous tile's store has read its buffer
+            mbar_arrive(&out_free[(local - 1) & 1u]);
+          }
+        }
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores complete before exit
+  } else {
+    // ------------------------------------------------------------ epilogue warps: thread = accumulator row
+    const int quarter = warp & 3;   // TMEM lane quarter this warp may read
+    const int cg = warp >> 2;       // column group
+    const int row = quarter * 32 + lane;   // row within the CTA's 128
+    const uint32_t acc_empty_leader = mapa_u32(smem_u32(&acc_empty[0]), 0);
+    uint32_t local = 0;
+    uint32_t aux_loads = 0;         // QKV: table loads consumed so far
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++local) {
+      const int n_blk = tile % num_n;
+      const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
+      const int n0 = n_blk * BN;
+      const uint32_t as = local & 1u;
+      const uint32_t use = local >> 1;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * kAccStride;
+      const int r = m0 + row;
+      const bool valid = r < p.M;
+
+      if constexpr (EPI == EPI_RESID) {
+        float* xbuf = reinterpret_cast<float*>(out_base);
+        uint8_t* xbbuf = out_base + 8 * kBox;
+        float* red = reinterpret_cast<float*>(aux_base);
+        mbar_wait(aux_full, local & 1u);          // residual tile landed (and the previous stores have drained)
+        mbar_wait(&acc_full[as], use & 1u);
+        tc_fence_after();
+        float ss = 0.f;
+        uint32_t pk[20];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int col = cg * 40 + half * 20;
+          uint32_t v[20];
+          tmem_ld16(taddr + col, v);
+          tmem_ld4(taddr + col + 16, v + 16);
+          float4* xrow = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(xbuf) + (cg * 2 + half) * kBox + row * 80);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            const float4 xo = xrow[j];
+            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col + 4 * j));
+            const float4 w = __ldg(reinterpret_cast<const float4*>(p.norm_w + n0 + col + 4 * j));
+            float4 f;
+            f.x = __uint_as_float(v[4 * j]) + b.x + xo.x;
+            f.y = __uint_as_float(v[4 * j + 1]) + b.y + xo.y;
+            f.z = __uint_as_float(v[4 * j + 2]) + b.z + xo.z;
+            f.w = __uint_as_float(v[4 * j + 3]) + b.w + xo.w;
+            ss = fmaf(f.x, f.x, ss); ss = fmaf(f.y, f.y, ss); ss = fmaf(f.z, f.z, ss); ss = fmaf(f.w, f.w, ss);
+            xrow[j] = f;                                              // new residual, in place
+            pk[half * 10 + 2 * j] = pack_bf16x2(f.x * w.x, f.y * w.y);   // x * w of the RMSNorm that reads x next
+            pk[half * 10 + 2 * j + 1] = pack_bf16x2(f.z * w.z, f.w * w.w);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(&acc_empty[as]); else mbar_arrive_cluster(acc_empty_leader + as * 8);
+        }
+        uint4* xbrow = reinterpret_cast<uint4*>(xbbuf + cg * kBox + row * 80);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) xbrow[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        red[cg * 128 + row] = ss;
+      } else if constexpr (EPI == EPI_QKV) {
+        // one head per column group; rotary pairs (d, d + 40) live in one thread's row
+        const int col0 = n0 + cg * 80;
+        const bool rot = col0 < 2 * (p.N / 3);   // q and k heads rotate, v heads do not
+        float rstd = 0.f;
+        if (valid) {
+          float s = 0.f;
+          for (int q = 0; q < p.ssq_parts; ++q) s += p.ssq_in[static_cast<int64_t>(q) * p.M + r];
+          rstd = rsqrtf(s * p.inv_dim + p.eps);
+        }
+        if (local == 0 || tile / num_n != (tile - 1) / num_n) {   // a new row block: its tables were (re)loaded
+          mbar_wait(aux_full, aux_loads & 1u);
+          ++aux_loads;
+        }
+        if (local > 0) mbar_wait(&out_free[0], (local - 1) & 1u);   // the previous tile's stores have drained
+        mbar_wait(&acc_full[as], use & 1u);
+        tc_fence_after();
+        const uint8_t* cs_row = aux_base + row * 80;
+        uint8_t* out_row = out_base + (cg * 2) * kBox + row * 80;
+#pragma unroll 1
+        for (int i0 = 0; i0 < 40; i0 += 8) {
+          uint32_t lo[8], hi[8];
+          tmem_ld8(taddr + cg * 80 + i0, lo);
+          tmem_ld8(taddr + cg * 80 + 40 + i0, hi);
+          float cs[8], sn[8];
+          if (rot) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              const int f4 = i0 / 4 + j;              // float4 index within the 40 angles: box f4 / 5, chunk f4 % 5
+              const int off = (f4 / 5) * kBox + (f4 % 5) * 16;
+              const float4 c4 = *reinterpret_cast<const float4*>(cs_row + off);
+              const float4 s4 = *reinterpret_cast<const float4*>(cs_row + 2 * kBox + off);
+              cs[4 * j] = c4.x; cs[4 * j + 1] = c4.y; cs[4 * j + 2] = c4.z; cs[4 * j + 3] = c4.w;
+              sn[4 * j] = s4.x; sn[4 * j + 1] = s4.y; sn[4 * j + 2] = s4.z; sn[4 * j + 3] = s4.w;
+            }
+          }
+          const float4 ba0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i0));
+          const float4 ba1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i0 + 4));
+          const float4 bb0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 40 + i0));
+          const float4 bb1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 40 + i0 + 4));
+          const float ba[8] = {ba0.x, ba0.y, ba0.z, ba0.w, ba1.x, ba1.y, ba1.z, ba1.w};
+          const float bb[8] = {bb0.x, bb0.y, bb0.z, bb0.w, bb1.x, bb1.y, bb1.z, bb1.w};
+          tmem_ld_wait();
+          float a[8], b[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            a[q] = fmaf(__uint_as_float(lo[q]), rstd, ba[q]);
+            b[q] = fmaf(__uint_as_float(hi[q]), rstd, bb[q]);
+          }
+          if (rot) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              // q*cos + rotate_half(q)*sin in fp32 (HF :161-166)
+              const float na = a[q] * cs[q] - b[q] * sn[q];
+              const float nb = b[q] * cs[q] + a[q] * sn[q];
+              a[q] = na;
+              b[q] = nb;
+            }
+          }
+          *reinterpret_cast<uint4*>(out_row + i0 * 2) =
+              make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
+          *reinterpret_cast<uint4*>(out_row + kBox + i0 * 2) =
+              make_uint4(pack_bf16x2(b[0], b[1]), pack_bf16x2(b[2], b[3]), pack_bf16x2(b[4], b[5]), pack_bf16x2(b[6], b[7]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(&acc_empty[as]); else mbar_arrive_cluster(acc_empty_leader + as * 8);
+        }
+      } else {  // EPI_SWIGLU
+        // tile columns [0,128) are gate rows, [128,256) the matching up rows; group cg owns 32 outputs
+        float rstd = 0.f;
+        if (valid) {
+          float s = 0.f;
+          for (int q = 0; q < p.ssq_parts; ++q) s += p.ssq_in[static_cast<int64_t>(q) * p.M + r];
+          rstd = rsqrtf(s * p.inv_dim + p.eps);
+        }
+        if (use > 0) mbar_wait(&out_free[as], (use - 1) & 1u);   // this buffer's previous store has drained
+        mbar_wait(&acc_full[as], use & 1u);
+        tc_fence_after();
+        // 128B-swizzled [128 x 64 bf16] boxes: 16-byte chunk index XOR (row & 7), as TMA SWIZZLE_128B expects
+        uint8_t* orow = out_base + as * 32768 + (cg >> 1) * 16384 + row * 128;
+#pragma unroll
+        for (int piece = 0; piece < 2; ++piece) {
+          const int c = cg * 32 + piece * 16;
+          uint32_t g[16], u[16];
+          tmem_ld16(taddr + c, g);
+          tmem_ld16(taddr + BN / 2 + c, u);
+          tmem_ld_wait();
+          float h[16];
+#pragma unroll
+          for (int q = 0; q < 16; q += 4) {
+            const float4 bg = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + q));
+            const float4 bu = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + BN / 2 + c + q));
+            h[q] = silu(fmaf(__uint_as_float(g[q]), rstd, bg.x)) * fmaf(__uint_as_float(u[q]), rstd, bu.x);
+            h[q + 1] = silu(fmaf(__uint_as_float(g[q + 1]), rstd, bg.y)) * fmaf(__uint_as_float(u[q + 1]), rstd, bu.y);
+            h[q + 2] = silu(fmaf(__uint_as_float(g[q + 2]), rstd, bg.z)) * fmaf(__uint_as_float(u[q + 2]), rstd, bu.z);
+            h[q + 3] = silu(fmaf(__uint_as_float(g[q + 3]), rstd, bg.w)) * fmaf(__uint_as_float(u[q + 3]), rstd, bu.w);
+          }
+          const int chunk = (cg & 1) * 4 + piece * 2;
+          *reinterpret_cast<uint4*>(orow + (((chunk) ^ (row & 7)) << 4)) =
+              make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+          *reinterpret_cast<uint4*>(orow + (((chunk + 1) ^ (row & 7)) << 4)) =
+              make_uint4(pack_bf16x2(h[8], h[9]), pack_bf16x2(h[10], h[11]), pack_bf16x2(h[12], h[13]), pack_bf16x2(h[14], h[15]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(&acc_empty[as]); else mbar_arrive_cluster(acc_empty_leader + as * 8);
+        }
+      }
+      // this warp's part of the tile is in shared memory: publish it to the async proxy, tell the store warp
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(store_ready);
+    }
+  }
+
+  // No CTA of the pair may exit (or free TMEM) while the other can still read its shared memory or arrive on its
+  // barriers.
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == kMmaWarp) tmem_dealloc_2cta(tmem_base, kTmemCols);
+}
+
+bool encode(CUtensorMap* map, CUtensorMapDataType dt, int elem, const void* base, uint64_t inner, uint64_t rows,
+            uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_rows, bool swizzle) {
+  return tma_encode_2d(map, static_cast<int>(dt), elem, base, inner, rows, row_stride_bytes, box_inner, box_rows, swizzle);
+}
+
+template <int EPI>
+cudaError_t launch2(const GemmArgs& a, int num_sms, cudaStream_t stream, const char** err) {
+  using L = Lay<EPI>;
+  CUtensorMap tmA, tmB, tm0, tm1, tm2;
+  bool ok = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.A, a.K, a.M, a.lda * 2, BK, BM, true) &&
+            encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.W, a.K, a.N, a.ldw * 2, BK, L::half_n, true);
+  if (EPI == EPI_QKV) {
+    ok = ok && encode(&tm0, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.out_bf16, a.N, a.M, a.ld_out * 2, 40, BM, false) &&
+         encode(&tm1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.cos_tab, 40, a.M, 160, 20, BM, false) &&
+         encode(&tm2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.sin_tab, 40, a.M, 160, 20, BM, false);
+  } else if (EPI == EPI_RESID) {
+    ok = ok && encode(&tm0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.x, a.N, a.M, a.ldx * 4, 20, BM, false) &&
+         encode(&tm1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.out_bf16, a.N, a.M, a.ld_out * 2, 40, BM, false);
+    tm2 = tm1;
+  } else {
+    ok = ok && encode(&tm0, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.out_bf16, a.N / 2, a.M, a.ld_out * 2, 64, BM, true);
+    tm1 = tm0;
+    tm2 = tm0;
+  }
+  if (!ok) {
+    *err = "cuTensorMapEncodeTiled failed (alignment or driver entry point)";
+    return cudaErrorInvalidValue;
+  }
+  static int max_clusters = 0;  // per template instantiation: co-resident CTA pairs on this device
+  if (max_clusters == 0) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::smem_bytes);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(num_sms & ~1);
+    cfg.blockDim = dim3(L::threads);
+    cfg.dynamicSmemBytes = L::smem_bytes;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    e = cudaOccupancyMaxActiveClusters(&n, gemm2_kernel<EPI>, &cfg);
+    if (e != cudaSuccess) return e;
+    if (n < 1) {
+      *err = "gemm2: no CTA pair fits on this device";
+      return cudaErrorInvalidValue;
+    }
+    max_clusters = n < num_sms / 2 ? n : num_sms / 2;
+  }
+  const int pair_tiles = ((a.M + 2 * BM - 1) / (2 * BM)) * (a.N / L::BN);
+  int clusters = max_clusters;
+  if (pair_tiles < clusters) clusters = pair_tiles;
+  gemm2_kernel<EPI><<<2 * clusters, L::threads, L::smem_bytes, stream>>>(tmA, tmB, tm0, tm1, tm2, a);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+bool gemm2_supports(const GemmArgs& a) {
+  if (a.A_lo != nullptr || a.row_map != nullptr) return false;
+  switch (a.epilogue) {
+    case EPI_QKV: return a.N % 240 == 0 && (a.N / 3) % 80 == 0;
+    case EPI_RESID: return (a.flags & GEMM_ADD_RESID) != 0 && a.N % 160 == 0 && a.bias != nullptr;
+    case EPI_SWIGLU: return a.N % 256 == 0;
+    default: return false;
+  }
+}
+
+int gemm2_resid_parts(int n) { return n / 160; }
+
+cudaError_t gemm2_launch(const GemmArgs& a, int num_sms, cudaStream_t stream, const char** err) {
+  switch (a.epilogue) {
+    case EPI_QKV: return launch2<EPI_QKV>(a, num_sms, stream, err);
+    case EPI_RESID: return launch2<EPI_RESID>(a, num_sms, stream, err);
+    case EPI_SWIGLU: return launch2<EPI_SWIGLU>(a, num_sms, stream, err);
+    default: *err = "gemm2: unsupported epilogue"; return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace vr2

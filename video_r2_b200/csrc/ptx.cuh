@@ -124,6 +124,87 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
       : "r"(taddr));
 }
 
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr));
+}
+
+// ---------------------------------------------------------------- clusters / CTA pairs (cta_group::2)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// All threads of both CTAs.
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address of this CTA -> shared::cluster address of the same offset in CTA `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(cta_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2cta(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2cta() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2cta(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B^T over the CTA pair: M = 256 (128 rows per CTA), each CTA holds half of B's rows.
+// Issued by ONE thread of the leader CTA (cluster rank 0).
+__device__ __forceinline__ void umma_bf16_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrives on the mbarrier at this offset in every CTA of `cta_mask` once the MMAs issued so far have retired.
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+// Tile load into THIS CTA's shared memory whose byte count completes on an mbarrier that may live in the
+// peer CTA (cluster address): the pair's loads are tracked by the leader's barrier.
+__device__ __forceinline__ void tma_load_2d_2cta(void* dst, const void* tmap, uint32_t bar_cluster_addr, int32_t c0,
+                                                 int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];"
+      :
+      : "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+// ---------------------------------------------------------------- TMA stores (shared -> global)
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               :
+               : "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// Waits until at most N of this thread's bulk groups still READ their shared-memory source.
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor for a K-major tile whose rows are 128 bytes
 // (64 bf16) wide and 128-byte swizzled exactly as TMA SWIZZLE_128B writes them:

@@ -131,7 +131,7 @@ extern "C" int vr2_tower_create(const vr2_tower_config* cfg, int32_t device, vr2
     return fail(VR2_ERR_ARG, "vr2_tower_create: bad depth/heads/hidden");
   const int head_dim = cfg->hidden_size / cfg->num_heads;
   if (head_dim != 80) return fail(VR2_ERR_ARG, "vr2_tower_create: head_dim %d unsupported (kernels are built for 80)", head_dim);
-  if (cfg->hidden_size % 256 != 0 || (3 * cfg->hidden_size) % 240 != 0)
+  if (cfg->hidden_size % 160 != 0 || (3 * cfg->hidden_size) % 240 != 0 || (cfg->hidden_size / 40) % 4 != 0)
     return fail(VR2_ERR_ARG, "vr2_tower_create: hidden_size %d must be a multiple of 1280", cfg->hidden_size);
   if (cfg->spatial_merge_size != 2) return fail(VR2_ERR_ARG, "vr2_tower_create: spatial_merge_size must be 2");
   if (cfg->out_hidden_size % 32 != 0) return fail(VR2_ERR_ARG, "vr2_tower_create: out_hidden_size must be a multiple of 32");
@@ -316,7 +316,7 @@ Workspace carve_ws(const vr2_tower* t, int64_t n, void* base) {
   w.qkv = reinterpret_cast<__nv_bfloat16*>(take(N * 3 * h * 2));
   w.att = reinterpret_cast<__nv_bfloat16*>(take(N * h * 2));
   w.hbuf = reinterpret_cast<__nv_bfloat16*>(take(N * std::max<size_t>(t->ipad, h) * 2));
-  w.ssq = reinterpret_cast<float*>(take(N * (h / 64) * 4));
+  w.ssq = reinterpret_cast<float*>(take(N * (h / 40) * 4));
   w.pix = reinterpret_cast<__nv_bfloat16*>(take(N * t->patch_k * 2));
   if (t->precision == VR2_PRECISION_SPLIT) {
     w.xb_lo = reinterpret_cast<__nv_bfloat16*>(take(N * h * 2));
@@ -360,11 +360,12 @@ extern "C" int vr2_tower_forward(vr2_tower* t, const vr2_plan* plan, const void*
     return fail(VR2_ERR_ARG, "vr2_tower_forward: workspace %zu < required %zu bytes", workspace_bytes, w.bytes);
   cudaStream_t s = as_stream(stream_v);
   const int h = t->cfg.hidden_size;
-  const int parts = h / 64;  // EPI_RESID writes one partial per 64-column group
+  int parts = 0;  // sum-of-squares partials per row written by the most recent EPI_RESID launch
   const float eps = t->cfg.rms_norm_eps;
   const char* msg = "";
   auto G = [&](const GemmArgs& a, int kind, const char* what) -> int {
     ProfScope prof(t, kind, s);
+    if (a.epilogue == EPI_RESID) parts = gemm_resid_parts(a);
     cudaError_t e = gemm_launch(a, t->num_sms, s, &msg);
     if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? VR2_ERR_ARG : VR2_ERR_CUDA, "vr2_tower_forward: %s: %s %s", what, cudaGetErrorString(e), msg);
     return VR2_OK;
