@@ -37,31 +37,39 @@ constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
 constexpr int kBox = 128 * 80;   // one [128 rows x 80 bytes] epilogue box (20 fp32 or 40 bf16 columns)
 
-template <int EPI>
+// V: reserved variant index (0 everywhere today).
+template <int EPI, int V>
 struct Cfg2;
 
 template <>
-struct Cfg2<EPI_QKV> {
+struct Cfg2<EPI_QKV, 0> {
   static constexpr int BN = 240, groups = 3, stages = 4;
   static constexpr int out_bytes = 6 * kBox;   // 3 heads x (first | second rotary half) boxes of 40 bf16 columns
   static constexpr int aux_bytes = 4 * kBox;   // cos: 2 boxes of 20 fp32 columns, sin: 2 boxes
 };
 template <>
-struct Cfg2<EPI_SWIGLU> {
+struct Cfg2<EPI_SWIGLU, 0> {
   static constexpr int BN = 256, groups = 4, stages = 5;
   static constexpr int out_bytes = 2 * 2 * 16384;  // double-buffered 128 x 128 bf16 as two 128B-swizzled 64-column boxes
   static constexpr int aux_bytes = 0;
 };
+// EPI_RESID moves its 128 x 160 tile through shared memory in four sub-steps of 40 columns, alternating between two
+// 30 KB buffers (fp32 residual: 2 boxes of 20 columns, updated in place; bf16 operand: 1 box of 40 columns), each
+// served by its own group of 8 epilogue warps: while one buffer is being computed on, the other one's stores drain
+// and its next residual piece loads.  Small buffers leave room for a 6-stage operand ring: the MMA main loop is
+// TMA-latency bound (ncu r01d: tensor pipe 29 % / 43 % with a 4-stage ring and whole-tile buffers).
+constexpr int kSubX = 2 * kBox;
+constexpr int kSubBytes = 3 * kBox;
 template <>
-struct Cfg2<EPI_RESID> {
-  static constexpr int BN = 160, groups = 4, stages = 4;
-  static constexpr int out_bytes = 8 * kBox + 4 * kBox;  // fp32 residual tile (in place) + bf16 operand tile
+struct Cfg2<EPI_RESID, 0> {
+  static constexpr int BN = 160, groups = 4, stages = 6;
+  static constexpr int out_bytes = 2 * kSubBytes;
   static constexpr int aux_bytes = 4 * 128 * 4;          // per column group partial sums of squares
 };
 
-template <int EPI>
+template <int EPI, int V>
 struct Lay {
-  using C = Cfg2<EPI>;
+  using C = Cfg2<EPI, V>;
   static constexpr int BN = C::BN;
   static constexpr int half_n = BN / 2;
   static constexpr int epi_warps = 4 * C::groups;
@@ -80,13 +88,13 @@ struct Lay {
 
 __device__ __forceinline__ float silu(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
-template <int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Lay<EPI>::threads, 1)
+template <int EPI, int V>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Lay<EPI, V>::threads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
              const __grid_constant__ CUtensorMap tm2, const GemmArgs p) {
-  using L = Lay<EPI>;
-  using C = Cfg2<EPI>;
+  using L = Lay<EPI, V>;
+  using C = Cfg2<EPI, V>;
   constexpr int BN = L::BN;
   constexpr int E = L::epi_warps;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -96,10 +104,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* empty_bar = full_bar + C::stages;
   uint64_t* acc_full = empty_bar + C::stages;
   uint64_t* acc_empty = acc_full + 2;
-  uint64_t* store_ready = acc_empty + 2;
-  uint64_t* out_free = store_ready + 1;   // [2]
-  uint64_t* aux_full = out_free + 2;      // residual tile / rotary tables landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + 1);
+  uint64_t* store_ready = acc_empty + 2;  // [2] (one per residual half buffer; [0] otherwise)
+  uint64_t* out_free = store_ready + 2;   // [2]
+  uint64_t* aux_full = out_free + 2;      // [2] residual half tile / rotary tables landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + 2);
   uint8_t* out_base = smem + L::out_off;
   uint8_t* aux_base = smem + L::aux_off;
 
@@ -135,9 +143,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], 2 * E);  // leader's: every epilogue warp of both CTAs
       mbar_init(&out_free[s], 1);
+      mbar_init(&store_ready[s], EPI == EPI_RESID ? E / 2 : E);
+      mbar_init(&aux_full[s], 1);
     }
-    mbar_init(store_ready, E);
-    mbar_init(aux_full, 1);
     fence_mbar_init();
   }
   if (warp == kMmaWarp) {
@@ -203,53 +211,70 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ------------------------------------------------------------ store warp: everything the epilogue moves by TMA
     uint32_t local = 0;
     if constexpr (EPI == EPI_RESID) {
+      // Sub-step st = 4 * (tile ordinal) + k covers tile columns [40k, 40k + 40) and uses buffer k & 1.  Per buffer:
+      //   load residual piece -> epilogue (in place) -> store x, xb -> stores have read the buffer -> load its next piece.
       float* red = reinterpret_cast<float*>(aux_base);
-      auto load_x = [&](int tile) {   // residual tile of `tile` -> out_base (8 boxes of 20 fp32 columns)
-        const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
-        const int n0 = (tile % num_n) * BN;
-        mbar_expect_tx(aux_full, 8 * kBox);
-        for (int b = 0; b < 8; ++b) tma_load_2d(out_base + b * kBox, &tm0, aux_full, n0 + b * 20, m0);
+      const int n_local = tile_begin < tile_end ? (tile_end - tile_begin + tile_step - 1) / tile_step : 0;
+      const int n_sub = 4 * n_local;
+      auto coords = [&](int st, int& m0, int& n0, int& n_blk) {
+        const int tile = tile_begin + (st >> 2) * tile_step;
+        m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
+        n_blk = tile % num_n;
+        n0 = n_blk * BN + (st & 3) * 40;
       };
-      if (lane == 0 && tile_begin < tile_end) load_x(tile_begin);
-      for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++local) {
-        const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
-        const int n_blk = tile % num_n;
-        const int n0 = n_blk * BN;
-        mbar_wait(store_ready, local & 1u);
+      auto load_x = [&](int st) {   // fp32 residual piece of sub-step st -> its buffer (2 boxes of 20 columns)
+        int m0, n0, n_blk;
+        coords(st, m0, n0, n_blk);
+        uint8_t* xb = out_base + (st & 1) * kSubBytes;
+        mbar_expect_tx(&aux_full[st & 1], kSubX);
+        tma_load_2d(xb, &tm0, &aux_full[st & 1], n0, m0);
+        tma_load_2d(xb + kBox, &tm0, &aux_full[st & 1], n0 + 20, m0);
+      };
+      if (lane == 0)
+        for (int st = 0; st < 2 && st < n_sub; ++st) load_x(st);
+      for (int st = 0; st < n_sub; ++st) {
+        int m0, n0, n_blk;
+        coords(st, m0, n0, n_blk);
+        const int b = st & 1;
+        mbar_wait(&store_ready[b], (st >> 1) & 1u);
         if (lane == 0) {
-          for (int b = 0; b < 8; ++b) tma_store_2d(&tm0, out_base + b * kBox, n0 + b * 20, m0);
-          for (int b = 0; b < 4; ++b) tma_store_2d(&tm1, out_base + (8 + b) * kBox, n0 + b * 40, m0);
+          const uint8_t* xb = out_base + b * kSubBytes;
+          tma_store_2d(&tm0, xb, n0, m0);
+          tma_store_2d(&tm0, xb + kBox, n0 + 20, m0);
+          tma_store_2d(&tm1, xb + kSubX, n0, m0);
           tma_store_commit();
         }
-        // sum of squares of the new residual rows over this tile's 160 columns: one value per (row, column block),
-        // part-major [N/160][M] so producers and consumers both touch it coalesced; fixed order -> deterministic
+        if ((st & 3) == 3) {
+          // sum of squares of the new residual rows over this tile's 160 columns: one value per (row, column block),
+          // part-major [N/160][M] so producers and consumers both touch it coalesced; fixed order -> deterministic
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int row = lane + 32 * k;
-          const float s = (red[row] + red[128 + row]) + (red[256 + row] + red[384 + row]);
-          if (m0 + row < p.M) p.ssq[static_cast<int64_t>(n_blk) * p.M + m0 + row] = s;
+          for (int k = 0; k < 4; ++k) {
+            const int row = lane + 32 * k;
+            const float sum = (red[row] + red[128 + row]) + (red[256 + row] + red[384 + row]);
+            if (m0 + row < p.M) p.ssq[static_cast<int64_t>(n_blk) * p.M + m0 + row] = sum;
+          }
+          __syncwarp();
         }
-        __syncwarp();
         if (lane == 0) {
-          tma_store_wait_read<0>();   // the stores have read the tile: the buffers may be refilled
-          if (tile + tile_step < tile_end) load_x(tile + tile_step);
+          tma_store_wait_read<0>();   // the stores have read the buffer: it may be refilled
+          if (st + 2 < n_sub) load_x(st + 2);
         }
       }
     } else if constexpr (EPI == EPI_QKV) {
       if (lane == 0) {
         auto load_cs = [&](int tile) {   // cos / sin rows of this CTA's 128 patches: 2 + 2 boxes of 20 fp32 columns
           const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
-          mbar_expect_tx(aux_full, 4 * kBox);
-          tma_load_2d(aux_base, &tm1, aux_full, 0, m0);
-          tma_load_2d(aux_base + kBox, &tm1, aux_full, 20, m0);
-          tma_load_2d(aux_base + 2 * kBox, &tm2, aux_full, 0, m0);
-          tma_load_2d(aux_base + 3 * kBox, &tm2, aux_full, 20, m0);
+          mbar_expect_tx(&aux_full[0], 4 * kBox);
+          tma_load_2d(aux_base, &tm1, &aux_full[0], 0, m0);
+          tma_load_2d(aux_base + kBox, &tm1, &aux_full[0], 20, m0);
+          tma_load_2d(aux_base + 2 * kBox, &tm2, &aux_full[0], 0, m0);
+          tma_load_2d(aux_base + 3 * kBox, &tm2, &aux_full[0], 20, m0);
         };
         if (tile_begin < tile_end) load_cs(tile_begin);
         for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++local) {
           const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
           const int n0 = (tile % num_n) * BN;
-          mbar_wait(store_ready, local & 1u);
+          mbar_wait(&store_ready[0], local & 1u);
           // every epilogue warp is done with the tables: fetch the next row block's if the rows change
           if (tile + 1 < tile_end && (tile + 1) / num_n != tile / num_n) load_cs(tile + 1);
           for (int b = 0; b < 6; ++b) tma_store_2d(&tm0, out_base + b * kBox, n0 + b * 40, m0);
@@ -263,7 +288,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++local) {
           const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
           const int n_blk = tile % num_n;
-          mbar_wait(store_ready, local & 1u);
+          mbar_wait(&store_ready[0], local & 1u);
           const uint8_t* ob = out_base + (local & 1u) * 32768;
           tma_store_2d(&tm0, ob, n_blk * (BN / 2), m0);
           tma_store_2d(&tm0, ob + 16384, n_blk * (BN / 2) + 64, m0);
@@ -295,47 +320,52 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const bool valid = r < p.M;
 
       if constexpr (EPI == EPI_RESID) {
-        float* xbuf = reinterpret_cast<float*>(out_base);
-        uint8_t* xbbuf = out_base + 8 * kBox;
+        // warp group g (8 warps) owns buffer g and the sub-steps k = g, g + 2 of every tile; inside a sub-step its two
+        // column halves c2 take 20 columns each (one fp32 box; half of the bf16 box)
         float* red = reinterpret_cast<float*>(aux_base);
-        mbar_wait(aux_full, local & 1u);          // residual tile landed (and the previous stores have drained)
-        mbar_wait(&acc_full[as], use & 1u);
-        tc_fence_after();
+        const int g = cg >> 1, c2 = cg & 1;
+        uint8_t* buf = out_base + g * kSubBytes;
+        float4* xrow = reinterpret_cast<float4*>(buf + c2 * kBox + row * 80);
+        uint2* xbrow = reinterpret_cast<uint2*>(buf + kSubX + row * 80 + c2 * 40);
         float ss = 0.f;
-        uint32_t pk[20];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int col = cg * 40 + half * 20;
+        for (int i = 0; i < 2; ++i) {
+          const int col = (g + 2 * i) * 40 + c2 * 20;
+          mbar_wait(&aux_full[g], (2 * local + i) & 1u);   // residual piece landed (the buffer's previous stores have drained)
+          if (i == 0) {
+            mbar_wait(&acc_full[as], use & 1u);
+            tc_fence_after();
+          }
           uint32_t v[20];
           tmem_ld16(taddr + col, v);
           tmem_ld4(taddr + col + 16, v + 16);
-          float4* xrow = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(xbuf) + (cg * 2 + half) * kBox + row * 80);
           tmem_ld_wait();
+          if (i == 1) {   // all of this warp's TMEM reads of the tile are complete
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (leader) mbar_arrive(&acc_empty[as]); else mbar_arrive_cluster(acc_empty_leader + as * 8);
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 5; ++j) {
             const float4 xo = xrow[j];
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col + 4 * j));
+            const float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col + 4 * j));
             const float4 w = __ldg(reinterpret_cast<const float4*>(p.norm_w + n0 + col + 4 * j));
             float4 f;
-            f.x = __uint_as_float(v[4 * j]) + b.x + xo.x;
-            f.y = __uint_as_float(v[4 * j + 1]) + b.y + xo.y;
-            f.z = __uint_as_float(v[4 * j + 2]) + b.z + xo.z;
-            f.w = __uint_as_float(v[4 * j + 3]) + b.w + xo.w;
+            f.x = __uint_as_float(v[4 * j]) + bi.x + xo.x;
+            f.y = __uint_as_float(v[4 * j + 1]) + bi.y + xo.y;
+            f.z = __uint_as_float(v[4 * j + 2]) + bi.z + xo.z;
+            f.w = __uint_as_float(v[4 * j + 3]) + bi.w + xo.w;
             ss = fmaf(f.x, f.x, ss); ss = fmaf(f.y, f.y, ss); ss = fmaf(f.z, f.z, ss); ss = fmaf(f.w, f.w, ss);
-            xrow[j] = f;                                              // new residual, in place
-            pk[half * 10 + 2 * j] = pack_bf16x2(f.x * w.x, f.y * w.y);   // x * w of the RMSNorm that reads x next
-            pk[half * 10 + 2 * j + 1] = pack_bf16x2(f.z * w.z, f.w * w.w);
+            xrow[j] = f;                                                         // new residual, in place
+            xbrow[j] = make_uint2(pack_bf16x2(f.x * w.x, f.y * w.y), pack_bf16x2(f.z * w.z, f.w * w.w));  // next GEMM's operand
           }
+          if (i == 1) red[cg * 128 + row] = ss;
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&store_ready[g]);
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (leader) mbar_arrive(&acc_empty[as]); else mbar_arrive_cluster(acc_empty_leader + as * 8);
-        }
-        uint4* xbrow = reinterpret_cast<uint4*>(xbbuf + cg * kBox + row * 80);
-#pragma unroll
-        for (int j = 0; j < 5; ++j) xbrow[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-        red[cg * 128 + row] = ss;
       } else if constexpr (EPI == EPI_QKV) {
         // one head per column group; rotary pairs (d, d + 40) live in one thread's row
         const int col0 = n0 + cg * 80;
@@ -347,7 +377,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           rstd = rsqrtf(s * p.inv_dim + p.eps);
         }
         if (local == 0 || tile / num_n != (tile - 1) / num_n) {   // a new row block: its tables were (re)loaded
-          mbar_wait(aux_full, aux_loads & 1u);
+          mbar_wait(&aux_full[0], aux_loads & 1u);
           ++aux_loads;
         }
         if (local > 0) mbar_wait(&out_free[0], (local - 1) & 1u);   // the previous tile's stores have drained
@@ -447,10 +477,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (leader) mbar_arrive(&acc_empty[as]); else mbar_arrive_cluster(acc_empty_leader + as * 8);
         }
       }
-      // this warp's part of the tile is in shared memory: publish it to the async proxy, tell the store warp
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(store_ready);
+      if constexpr (EPI != EPI_RESID) {
+        // this warp's part of the tile is in shared memory: publish it to the async proxy, tell the store warp
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&store_ready[0]);
+      }
     }
   }
 
@@ -466,9 +498,9 @@ bool encode(CUtensorMap* map, CUtensorMapDataType dt, int elem, const void* base
   return tma_encode_2d(map, static_cast<int>(dt), elem, base, inner, rows, row_stride_bytes, box_inner, box_rows, swizzle);
 }
 
-template <int EPI>
+template <int EPI, int V>
 cudaError_t launch2(const GemmArgs& a, int num_sms, cudaStream_t stream, const char** err) {
-  using L = Lay<EPI>;
+  using L = Lay<EPI, V>;
   CUtensorMap tmA, tmB, tm0, tm1, tm2;
   bool ok = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.A, a.K, a.M, a.lda * 2, BK, BM, true) &&
             encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.W, a.K, a.N, a.ldw * 2, BK, L::half_n, true);
@@ -491,7 +523,7 @@ cudaError_t launch2(const GemmArgs& a, int num_sms, cudaStream_t stream, const c
   }
   static int max_clusters = 0;  // per template instantiation: co-resident CTA pairs on this device
   if (max_clusters == 0) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<EPI, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::smem_bytes);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(num_sms & ~1);
@@ -505,7 +537,7 @@ cudaError_t launch2(const GemmArgs& a, int num_sms, cudaStream_t stream, const c
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
     int n = 0;
-    e = cudaOccupancyMaxActiveClusters(&n, gemm2_kernel<EPI>, &cfg);
+    e = cudaOccupancyMaxActiveClusters(&n, gemm2_kernel<EPI, V>, &cfg);
     if (e != cudaSuccess) return e;
     if (n < 1) {
       *err = "gemm2: no CTA pair fits on this device";
@@ -516,7 +548,7 @@ cudaError_t launch2(const GemmArgs& a, int num_sms, cudaStream_t stream, const c
   const int pair_tiles = ((a.M + 2 * BM - 1) / (2 * BM)) * (a.N / L::BN);
   int clusters = max_clusters;
   if (pair_tiles < clusters) clusters = pair_tiles;
-  gemm2_kernel<EPI><<<2 * clusters, L::threads, L::smem_bytes, stream>>>(tmA, tmB, tm0, tm1, tm2, a);
+  gemm2_kernel<EPI, V><<<2 * clusters, L::threads, L::smem_bytes, stream>>>(tmA, tmB, tm0, tm1, tm2, a);
   return cudaGetLastError();
 }
 
@@ -536,9 +568,9 @@ int gemm2_resid_parts(int n) { return n / 160; }
 
 cudaError_t gemm2_launch(const GemmArgs& a, int num_sms, cudaStream_t stream, const char** err) {
   switch (a.epilogue) {
-    case EPI_QKV: return launch2<EPI_QKV>(a, num_sms, stream, err);
-    case EPI_RESID: return launch2<EPI_RESID>(a, num_sms, stream, err);
-    case EPI_SWIGLU: return launch2<EPI_SWIGLU>(a, num_sms, stream, err);
+    case EPI_QKV: return launch2<EPI_QKV, 0>(a, num_sms, stream, err);
+    case EPI_RESID: return launch2<EPI_RESID, 0>(a, num_sms, stream, err);
+    case EPI_SWIGLU: return launch2<EPI_SWIGLU, 0>(a, num_sms, stream, err);
     default: *err = "gemm2: unsupported epilogue"; return cudaErrorInvalidValue;
   }
 }
