@@ -1,0 +1,437 @@
+// Variable-length, non-causal attention on the 5th-generation tensor cores (tcgen05 / TMEM / TMA) for the vision
+// tower (HF modeling_qwen2_5_vl.py:221-287): window layers attend inside cu_window_seqlens segments (<= 64 patches),
+// layers 7/15/23/31 inside one temporal slice (h*w patches).  q/k/v: bf16, 16 heads x 80, one [N, 3840] buffer
+// written by the QKV GEMM epilogue (rotary already applied).
+//
+// Work item = (128-row query tile, head).  Every patch row r carries the bounds [lo_r, hi_r) of its segment (plan:
+// seg_window / seg_full), so one kernel serves both kinds of layer and ragged batches: the tile visits the 128-row
+// key/value blocks that cover [lo of its first row, hi of its last row) and each row masks what is outside its own
+// segment.  With 64-patch windows a tile is exactly two windows and one key block.
+//
+// Persistent CTAs, 6 warps:
+//   warp 4 (one lane)  TMA producer: Q once per item, K|V blocks into a 3-stage ring.  A 128 x 80 operand tile is
+//                      two boxes: 64 columns (128-byte swizzle) + 16 columns (32-byte swizzle).
+//   warp 5 (one lane)  tcgen05.mma issuer:  S_j = Q K_j^T (5 MMAs of 128x128x16 into one of two TMEM S buffers),
+//                      O_j = P_j V_j (8 k-steps x {N=64, N=16}, V as an MN-major operand, fresh accumulator per block)
+//   warps 0-3          softmax, thread = query row = TMEM lane: row max, exp2, P_j -> shared memory (bf16, the
+//                      K-major 128B-swizzled layout the MMA reads), running max / sum; the block outputs O_j are
+//                      folded into 80 fp32 registers per row with the usual rescale, one block behind the MMAs so
+//                      the softmax of block j+1 overlaps P_j V_j.  Result -> shared memory -> one TMA store.
+// fp32 scores, softmax and accumulation; bf16 operands (P is rounded to bf16 like q, k, v).
+#include "attention.cuh"
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <mutex>
+
+#include "gemm.cuh"
+#include "ptx.cuh"
+
+namespace vr2 {
+
+namespace {
+
+constexpr int HD = 80;
+constexpr int TQ = 128;
+constexpr int TK = 128;
+constexpr int KV_STAGES = 3;
+constexpr int Q64_BYTES = TQ * 128;          // [128 x 64 bf16], SWIZZLE_128B
+constexpr int Q16_BYTES = TQ * 32;           // [128 x 16 bf16], SWIZZLE_32B
+constexpr int TILE_BYTES = Q64_BYTES + Q16_BYTES;     // 20 KB: one 128 x 80 operand tile
+constexpr int KV_STAGE_BYTES = 2 * TILE_BYTES;        // K tile | V tile
+constexpr int P_BYTES = 2 * TQ * 128;                 // [128 x 128 bf16] as two 64-column SWIZZLE_128B atoms
+constexpr int OUT_BYTES = 2 * TQ * 80;                // two [128 x 40 bf16] boxes, 80-byte rows
+
+constexpr int OFF_Q = 0;
+constexpr int OFF_KV = OFF_Q + TILE_BYTES;
+constexpr int OFF_P = OFF_KV + KV_STAGES * KV_STAGE_BYTES;
+constexpr int OFF_OUT = OFF_P + 2 * P_BYTES;
+constexpr int OFF_BAR = OFF_OUT + OUT_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 256;
+static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared-memory limit");
+
+constexpr int TM_S = 0;      // two S buffers: columns [0,128), [128,256)
+constexpr int TM_O = 256;    // two O buffers: columns [256,336), [384,464)
+constexpr int TM_O_STRIDE = 128;
+
+// K-major operand tile with 32-byte rows (16 bf16 = one MMA k-step), SWIZZLE_32B: 8-row groups every 256 bytes
+__device__ __forceinline__ uint64_t desc_k_sw32(uint32_t addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(256 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(6) << 61;   // SWIZZLE_32B
+  return d;
+}
+// MN-major operand (V as B: rows = key index = MMA K, columns = head dim = MMA N), 128-byte rows of 64 columns,
+// SWIZZLE_128B: the 8 k-rows of an atom are 128 bytes apart, atoms along K every 1024 bytes (SBO); a single
+// 64-column chunk along N, so LBO is unused.
+__device__ __forceinline__ uint64_t desc_mn_sw128(uint32_t addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+// same for the 16-column remainder: 32-byte rows, SWIZZLE_32B, atoms along K every 256 bytes
+__device__ __forceinline__ uint64_t desc_mn_sw32(uint32_t addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(256 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(6) << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t idesc_bf16(int m, int n, bool b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (b_mn_major ? (1u << 16) : 0u) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(m >> 4) << 24);
+}
+__device__ __forceinline__ float ex2_approx(float x) {   // MUFU.EX2: 2 ulp, exact 0 for -inf
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+__global__ void __launch_bounds__(192, 1)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUtensorMap tm16,
+               const __grid_constant__ CUtensorMap tmOut, const int2* __restrict__ seg, int n_rows, int num_heads,
+               int hidden, float scale_log2) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* q_empty = q_full + 1;
+  uint64_t* kv_full = q_empty + 1;          // [KV_STAGES]
+  uint64_t* kv_empty = kv_full + KV_STAGES; // [KV_STAGES]
+  uint64_t* s_full = kv_empty + KV_STAGES;  // [2]
+  uint64_t* p_ready = s_full + 2;           // [2]
+  uint64_t* o_full = p_ready + 2;           // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tiles = (n_rows + TQ - 1) / TQ;
+  const int n_items = n_tiles * num_heads;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tm64);
+    tma_prefetch_desc(&tm16);
+    tma_prefetch_desc(&tmOut);
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int s = 0; s < KV_STAGES; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&s_full[s], 1);
+      mbar_init(&p_ready[s], 4);   // one arrive per softmax warp
+      mbar_init(&o_full[s], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // key/value block range of a query tile: from the segment start of its first row to the segment end of its last
+  auto kv_range = [&](int tile, int& kv_lo, int& nblk) {
+    const int r0 = tile * TQ;
+    const int r1 = min(r0 + TQ, n_rows) - 1;
+    kv_lo = seg[r0].x;
+    nblk = (seg[r1].y - kv_lo + TK - 1) / TK;
+  };
+
+  if (warp == 4) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t it = 0, item_no = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_no) {
+        const int tile = item / num_heads, head = item % num_heads;
+        int kv_lo, nblk;
+        kv_range(tile, kv_lo, nblk);
+        mbar_wait(q_empty, (item_no & 1u) ^ 1u);     // the previous item's S MMAs have read Q
+        mbar_expect_tx(q_full, TILE_BYTES);
+        tma_load_2d(smem + OFF_Q, &tm64, q_full, head * HD, tile * TQ);
+        tma_load_2d(smem + OFF_Q + Q64_BYTES, &tm16, q_full, head * HD + 64, tile * TQ);
+        for (int j = 0; j < nblk; ++j, ++it) {
+          const uint32_t s = it % KV_STAGES, ph = (it / KV_STAGES) & 1u;
+          mbar_wait(&kv_empty[s], ph ^ 1u);
+          uint8_t* kb = smem + OFF_KV + s * KV_STAGE_BYTES;
+          const int row = kv_lo + j * TK;
+          mbar_expect_tx(&kv_full[s], KV_STAGE_BYTES);
+          tma_load_2d(kb, &tm64, &kv_full[s], hidden + head * HD, row);
+          tma_load_2d(kb + Q64_BYTES, &tm16, &kv_full[s], hidden + head * HD + 64, row);
+          tma_load_2d(kb + TILE_BYTES, &tm64, &kv_full[s], 2 * hidden + head * HD, row);
+          tma_load_2d(kb + TILE_BYTES + Q64_BYTES, &tm16, &kv_full[s], 2 * hidden + head * HD + 64, row);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t id_s = idesc_bf16(TQ, TK, false);
+      constexpr uint32_t id_o64 = idesc_bf16(TQ, 64, true);
+      constexpr uint32_t id_o16 = idesc_bf16(TQ, 16, true);
+      const uint32_t q_addr = smem_u32(smem + OFF_Q);
+      uint32_t it = 0;      // kv ring position of the NEXT block whose S has not been issued
+      uint32_t blk = 0;     // global block counter: S / P / O buffer = blk & 1
+      uint32_t item_no = 0;
+      auto issue_s = [&](uint32_t stage, uint32_t b) {   // S_b = Q K^T
+        const uint32_t k_addr = smem_u32(smem + OFF_KV + stage * KV_STAGE_BYTES);
+        const uint32_t d = tmem_base + TM_S + (b & 1u) * TK;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(d, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), id_s, k != 0 ? 1u : 0u);
+        umma_bf16(d, desc_k_sw32(q_addr + Q64_BYTES), desc_k_sw32(k_addr + Q64_BYTES), id_s, 1u);
+        umma_commit(&s_full[b & 1u]);
+      };
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_no) {
+        const int tile = item / num_heads;
+        int kv_lo, nblk;
+        kv_range(tile, kv_lo, nblk);
+        mbar_wait(q_full, item_no & 1u);
+        // first S of the item
+        {
+          const uint32_t s = it % KV_STAGES, ph = (it / KV_STAGES) & 1u;
+          mbar_wait(&kv_full[s], ph);
+          tc_fence_after();
+          issue_s(s, blk);
+        }
+        for (int j = 0; j < nblk; ++j) {
+          const uint32_t s = (it + j) % KV_STAGES;
+          const uint32_t b = blk + j;
+          if (j + 1 < nblk) {   // S of the next block runs while the softmax warps work on this one
+            const uint32_t s1 = (it + j + 1) % KV_STAGES, ph1 = ((it + j + 1) / KV_STAGES) & 1u;
+            mbar_wait(&kv_full[s1], ph1);
+            tc_fence_after();
+            issue_s(s1, b + 1);
+          } else {
+            umma_commit(q_empty);   // every S MMA of this item has been issued: Q is free once they retire
+          }
+          mbar_wait(&p_ready[b & 1u], (b >> 1) & 1u);   // P_j is in shared memory (and O buffer b&1 has been consumed)
+          tc_fence_after();
+          const uint32_t p_addr = smem_u32(smem + OFF_P + (b & 1u) * P_BYTES);
+          const uint32_t v_addr = smem_u32(smem + OFF_KV + s * KV_STAGE_BYTES + TILE_BYTES);
+          const uint32_t d = tmem_base + TM_O + (b & 1u) * TM_O_STRIDE;
+#pragma unroll
+          for (int kk = 0; kk < TK / 16; ++kk) {
+            const uint64_t da = umma_desc_sw128(p_addr + (kk >> 2) * (TQ * 128) + (kk & 3) * 32);
+            umma_bf16(d, da, desc_mn_sw128(v_addr + kk * 2048), id_o64, kk != 0 ? 1u : 0u);
+            umma_bf16(d + 64, da, desc_mn_sw32(v_addr + Q64_BYTES + kk * 512), id_o16, kk != 0 ? 1u : 0u);
+          }
+          umma_commit(&kv_empty[s]);        // K_j (read by S_j earlier) and V_j are free once these retire
+          umma_commit(&o_full[b & 1u]);
+        }
+        it += nblk;
+        blk += nblk;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ softmax warps: thread = query row = TMEM lane
+    const int tid = threadIdx.x;              // 0..127
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+    uint32_t blk = 0;
+    uint32_t item_no = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_no) {
+      const int tile = item / num_heads, head = item % num_heads;
+      int kv_lo, nblk;
+      kv_range(tile, kv_lo, nblk);
+      const int r = tile * TQ + tid;
+      int lo = 0, hi = 0;
+      if (r < n_rows) {
+        const int2 sg = seg[r];
+        lo = sg.x;
+        hi = sg.y;
+      }
+      float o[HD];
+#pragma unroll
+      for (int i = 0; i < HD; ++i) o[i] = 0.f;
+      float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
+
+      auto fold = [&](uint32_t b, float corr) {   // o = o * corr + O_b
+        mbar_wait(&o_full[b & 1u], (b >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t ta = lane_addr + TM_O + (b & 1u) * TM_O_STRIDE;
+        uint32_t v[HD];
+        tmem_ld32(ta, v);
+        tmem_ld32(ta + 32, v + 32);
+        tmem_ld16(ta + 64, v + 64);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < HD; ++i) o[i] = fmaf(o[i], corr, __uint_as_float(v[i]));
+        tc_fence_before();
+      };
+
+      for (int j = 0; j < nblk; ++j) {
+        const uint32_t b = blk + j;
+        const int c_lo = lo - (kv_lo + j * TK), c_hi = hi - (kv_lo + j * TK);   // this row's valid columns of the block
+        const uint32_t ts = lane_addr + TM_S + (b & 1u) * TK;
+        mbar_wait(&s_full[b & 1u], (b >> 1) & 1u);
+        tc_fence_after();
+        // Each 64-column half of the block is, for this row, entirely inside its segment (no masking), entirely
+        // outside (skipped: P = 0) or cut by a segment boundary (masked element by element).
+        // pass 1: row maximum over the valid columns (64 columns per TMEM round trip)
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c0 = 0; c0 < TK; c0 += 64) {
+          // tcgen05.ld is warp-collective: a half is skipped only when it is outside for every row of the warp
+          const bool outside = c_hi <= c0 || c_lo >= c0 + 64;
+          if (__all_sync(0xffffffffu, outside)) continue;
+          const bool interior = c_lo <= c0 && c_hi >= c0 + 64;
+          uint32_t v[64];
+          tmem_ld32(ts + c0, v);
+          tmem_ld32(ts + c0 + 32, v + 32);
+          tmem_ld_wait();
+          if (outside) {
+          } else if (interior) {
+            float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]), m3 = __uint_as_float(v[3]);
+#pragma unroll
+            for (int i = 4; i < 64; i += 4) {
+              m0 = fmaxf(m0, __uint_as_float(v[i]));
+              m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+              m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
+              m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
+            }
+            mx = fmaxf(mx, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) {
+              const int c = c0 + i;
+              if (c >= c_lo && c < c_hi) mx = fmaxf(mx, __uint_as_float(v[i]));
+            }
+          }
+        }
+        const float m_new = fmaxf(m_run, mx);
+        // exp2((s - m) * scale): scores stay unscaled in TMEM, the 1/sqrt(d) * log2(e) factor is applied here
+        const float m_scaled = m_new == -INFINITY ? 0.f : m_new * scale_log2;
+        const float corr = m_run == -INFINITY ? 0.f : ex2_approx(m_run * scale_log2 - m_scaled);
+        m_run = m_new;
+        // pass 2: probabilities -> bf16 -> shared memory in the K-major SWIZZLE_128B layout the P V MMAs read
+        uint8_t* prow = smem + OFF_P + (b & 1u) * P_BYTES + tid * 128;
+        float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < TK; c0 += 64) {
+          uint8_t* atom = prow + (c0 >> 6) * (TQ * 128);     // 64 key columns = one swizzle atom row of 128 bytes
+          const bool outside = c_hi <= c0 || c_lo >= c0 + 64;
+          if (__all_sync(0xffffffffu, outside)) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(atom + ((q ^ (tid & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+            continue;
+          }
+          const bool interior = c_lo <= c0 && c_hi >= c0 + 64;
+          uint32_t v[64];
+          tmem_ld32(ts + c0, v);
+          tmem_ld32(ts + c0 + 32, v + 32);
+          tmem_ld_wait();
+          uint32_t pk[32];
+          if (outside) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) pk[i] = 0u;
+          } else if (interior) {
+#pragma unroll
+            for (int i = 0; i < 64; i += 2) {
+              const float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), scale_log2, -m_scaled));
+              const float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), scale_log2, -m_scaled));
+              rs0 += p0;
+              rs1 += p1;
+              pk[i >> 1] = pack_bf16x2(p0, p1);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 64; i += 2) {
+              const int c = c0 + i;
+              const float p0 = (c >= c_lo && c < c_hi) ? ex2_approx(fmaf(__uint_as_float(v[i]), scale_log2, -m_scaled)) : 0.f;
+              const float p1 = (c + 1 >= c_lo && c + 1 < c_hi) ? ex2_approx(fmaf(__uint_as_float(v[i + 1]), scale_log2, -m_scaled)) : 0.f;
+              rs0 += p0;
+              rs1 += p1;
+              pk[i >> 1] = pack_bf16x2(p0, p1);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<uint4*>(atom + ((q ^ (tid & 7)) << 4)) =
+                make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        }
+        const float rs = rs0 + rs1;
+        l_run = l_run * corr + rs;
+        tc_fence_before();       // this thread's TMEM reads of S_b are complete (tcgen05.wait::ld above)
+        fence_proxy_async();     // P_b visible to the tensor core's shared-memory reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[b & 1u]);
+        // fold the previous block's output in while the tensor core works on this one
+        if (j > 0) fold(b - 1, corr_prev);
+        corr_prev = corr;
+      }
+      fold(blk + nblk - 1, corr_prev);
+      blk += nblk;
+
+      // ---- normalise, stage [128 x 80] bf16 (two 40-column boxes, 80-byte rows: conflict-free), one TMA store
+      const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+      if (tid == 0) tma_store_wait_read<0>();    // the previous item's store has read the staging buffer
+      named_bar_sync(1, 128);
+      uint8_t* orow = smem + OFF_OUT + tid * 80;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+          const int i = half * 40 + q * 8;
+          *reinterpret_cast<uint4*>(orow + half * (TQ * 80) + q * 16) =
+              make_uint4(pack_bf16x2(o[i] * inv, o[i + 1] * inv), pack_bf16x2(o[i + 2] * inv, o[i + 3] * inv),
+                         pack_bf16x2(o[i + 4] * inv, o[i + 5] * inv), pack_bf16x2(o[i + 6] * inv, o[i + 7] * inv));
+        }
+      }
+      fence_proxy_async();
+      named_bar_sync(1, 128);
+      if (tid == 0) {
+        tma_store_2d(&tmOut, smem + OFF_OUT, head * HD, tile * TQ);
+        tma_store_2d(&tmOut, smem + OFF_OUT + TQ * 80, head * HD + 40, tile * TQ);
+        tma_store_commit();
+      }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+cudaError_t attention_tc_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, const int2* seg, int n_rows, int num_heads,
+                                int64_t ld_qkv, int64_t ld_out, int num_sms, cudaStream_t stream) {
+  if (n_rows <= 0) return cudaSuccess;
+  const int hidden = num_heads * HD;
+  CUtensorMap tm64, tm16, tmOut;
+  if (!tma_encode_2d(&tm64, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, qkv, 3 * hidden, n_rows, ld_qkv * 2, 64, TQ, true) ||
+      !tma_encode_2d_swz(&tm16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, qkv, 3 * hidden, n_rows, ld_qkv * 2, 16, TQ, 32) ||
+      !tma_encode_2d(&tmOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, out, hidden, n_rows, ld_out * 2, 40, TQ, false))
+    return cudaErrorInvalidValue;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  });
+  if (attr_err != cudaSuccess) return attr_err;
+  const int items = ((n_rows + TQ - 1) / TQ) * num_heads;
+  const int grid = items < num_sms ? items : num_sms;
+  const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
+  attn_tc_kernel<<<grid, 192, SMEM_BYTES, stream>>>(tm64, tm16, tmOut, seg, n_rows, num_heads, hidden, scale_log2);
+  return cudaGetLastError();
+}
+
+}  // namespace vr2

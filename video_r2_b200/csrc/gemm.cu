@@ -657,19 +657,28 @@ cudaError_t launch_any(const GemmArgs& a, int num_sms, cudaStream_t stream, cons
 
 }  // namespace
 
-bool tma_encode_2d(CUtensorMap* map, int dtype, int elem_bytes, const void* base, uint64_t inner, uint64_t rows,
-                   uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_rows, bool swizzle128) {
+bool tma_encode_2d_swz(CUtensorMap* map, int dtype, const void* base, uint64_t inner, uint64_t rows,
+                       uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_rows, int swizzle_bytes) {
   EncodeFn fn = resolve_encode();
   if (fn == nullptr) return false;
-  (void)elem_bytes;
   const cuuint64_t dims[2] = {inner, rows};
   const cuuint64_t strides[1] = {row_stride_bytes};
   const cuuint32_t box[2] = {box_inner, box_rows};
   const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                              : swizzle_bytes == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
+                              : swizzle_bytes == 32  ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                     : CU_TENSOR_MAP_SWIZZLE_NONE;
   CUresult r = fn(map, static_cast<CUtensorMapDataType>(dtype), 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
-                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
+}
+
+bool tma_encode_2d(CUtensorMap* map, int dtype, int elem_bytes, const void* base, uint64_t inner, uint64_t rows,
+                   uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_rows, bool swizzle128) {
+  (void)elem_bytes;
+  return tma_encode_2d_swz(map, dtype, base, inner, rows, row_stride_bytes, box_inner, box_rows, swizzle128 ? 128 : 0);
 }
 
 bool tma_encode_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,

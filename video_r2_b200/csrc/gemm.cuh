@@ -68,6 +68,10 @@ cudaError_t gemm2_launch(const GemmArgs& args, int num_sms, cudaStream_t stream,
 bool tma_encode_2d(CUtensorMap* map, int dtype, int elem_bytes, const void* base, uint64_t inner, uint64_t rows,
                    uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_rows, bool swizzle128);
 
+// swizzle_bytes: 0 (none), 32, 64 or 128
+bool tma_encode_2d_swz(CUtensorMap* map, int dtype, const void* base, uint64_t inner, uint64_t rows,
+                       uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_rows, int swizzle_bytes);
+
 // Resolves cuTensorMapEncodeTiled through the runtime (no link against libcuda).
 bool tma_encode_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
                         uint32_t box_inner, uint32_t box_rows);

@@ -181,7 +181,13 @@ extern "C" int vr2_plan_create(const vr2_plan_config* cfg, const int64_t* grid, 
 
   const size_t N = plan->n_patches, T = plan->n_tokens, HDIM = plan->half_dim;
   auto rnd = [](size_t b) { return (b + 255) & ~static_cast<size_t>(255); };
-  const size_t total = rnd(T * 8) * 2 + rnd(N * 4) + rnd(T * 4) + rnd(N * 8) + rnd(N * HDIM * 4) * 2 +
+  // per-row segment bounds for the tcgen05 attention kernel (attention2.cu): expanded from the cu arrays
+  std::vector<int2> seg_w(N), seg_f(N);
+  for (size_t i = 0; i + 1 < cu_window.size(); ++i)
+    for (int r = cu_window[i]; r < cu_window[i + 1]; ++r) seg_w[r] = make_int2(cu_window[i], cu_window[i + 1]);
+  for (size_t i = 0; i + 1 < cu_seq.size(); ++i)
+    for (int r = cu_seq[i]; r < cu_seq[i + 1]; ++r) seg_f[r] = make_int2(cu_seq[i], cu_seq[i + 1]);
+  const size_t total = rnd(N * 8) * 2 + rnd(T * 8) * 2 + rnd(N * 4) + rnd(T * 4) + rnd(N * 8) + rnd(N * HDIM * 4) * 2 +
                        rnd(cu_window.size() * 4) + rnd(cu_seq.size() * 4) + rnd(tiles_w.size() * 16) +
                        rnd(tiles_f.size() * 16) + rnd(clips.size() * sizeof(ClipDesc)) + rnd(inv_freq.size() * 4);
   e = cudaMalloc(&plan->blob, total);
@@ -201,6 +207,8 @@ extern "C" int vr2_plan_create(const vr2_plan_config* cfg, const int64_t* grid, 
   plan->cu_seqlens = carve<int32_t>(cur, cu_seq.size());
   plan->tiles_window = carve<int4>(cur, tiles_w.size());
   plan->tiles_full = carve<int4>(cur, tiles_f.size());
+  plan->seg_window = carve<int2>(cur, N);
+  plan->seg_full = carve<int2>(cur, N);
   ClipDesc* d_clips = carve<ClipDesc>(cur, clips.size());
   float* d_inv = carve<float>(cur, inv_freq.size());
 
@@ -209,6 +217,8 @@ extern "C" int vr2_plan_create(const vr2_plan_config* cfg, const int64_t* grid, 
   if (e == cudaSuccess) e = up(plan->cu_seqlens, cu_seq.data(), cu_seq.size() * 4);
   if (e == cudaSuccess) e = up(plan->tiles_window, tiles_w.data(), tiles_w.size() * 16);
   if (e == cudaSuccess) e = up(plan->tiles_full, tiles_f.data(), tiles_f.size() * 16);
+  if (e == cudaSuccess) e = up(plan->seg_window, seg_w.data(), N * 8);
+  if (e == cudaSuccess) e = up(plan->seg_full, seg_f.data(), N * 8);
   if (e == cudaSuccess) e = up(d_clips, clips.data(), clips.size() * sizeof(ClipDesc));
   if (e == cudaSuccess) e = up(d_inv, inv_freq.data(), inv_freq.size() * 4);
   if (e == cudaSuccess) {

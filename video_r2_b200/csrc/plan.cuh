@@ -28,6 +28,8 @@ struct vr2_plan {
   float* sin_tab = nullptr;
   int32_t* cu_window = nullptr;      // [windows+1]
   int32_t* cu_seqlens = nullptr;     // [slices+1]
-  int4* tiles_window = nullptr;      // attention query tiles for window layers
+  int4* tiles_window = nullptr;      // attention query tiles for window layers (mma.sync kernel, split precision)
   int4* tiles_full = nullptr;        // ... for full-attention layers
+  int2* seg_window = nullptr;        // [patches] (first, past-last) row of the window a patch row belongs to
+  int2* seg_full = nullptr;          // [patches] ... of its temporal slice (tcgen05 attention kernel)
 };

@@ -410,9 +410,13 @@ extern "C" int vr2_tower_forward(vr2_tower* t, const vr2_plan* plan, const void*
     {
       const bool full = is_full_layer(t, l);
       ProfScope prof(t, full ? VR2_K_ATTN_FULL : VR2_K_ATTN_WINDOW, s);
-      VR2_CUDA(attention_launch(w.qkv, w.qkv_lo, w.att, w.att_lo, full ? plan->tiles_full : plan->tiles_window,
-                                static_cast<int>(full ? plan->n_tiles_full : plan->n_tiles_window), t->cfg.num_heads,
-                                3 * h, h, s));
+      if (split)   // hi + lo operands: the mma.sync kernel with 3 products per contraction
+        VR2_CUDA(attention_launch(w.qkv, w.qkv_lo, w.att, w.att_lo, full ? plan->tiles_full : plan->tiles_window,
+                                  static_cast<int>(full ? plan->n_tiles_full : plan->n_tiles_window), t->cfg.num_heads,
+                                  3 * h, h, s));
+      else
+        VR2_CUDA(attention_tc_launch(w.qkv, w.att, full ? plan->seg_full : plan->seg_window, static_cast<int>(N),
+                                     t->cfg.num_heads, 3 * h, h, t->num_sms, s));
     }
     {
       GemmArgs a{};
@@ -574,21 +578,42 @@ extern "C" int vr2_op_attention_split(const void* qkv_hi, const void* qkv_lo, vo
 static int op_attention_impl(const void* qkv, const void* qkv_lo, void* out, void* out_lo, const int32_t* cu,
                              int32_t n_seq, int32_t num_heads, void* stream_v) {
   if (qkv == nullptr || out == nullptr || cu == nullptr || n_seq <= 0) return fail(VR2_ERR_ARG, "vr2_op_attention: null pointer");
-  std::vector<int4> tiles;
-  for (int i = 0; i < n_seq; ++i) {
-    const int s0 = cu[i], L = cu[i + 1] - cu[i];
-    if (L < 0) return fail(VR2_ERR_ARG, "vr2_op_attention: cu_seqlens not monotone");
-    for (int q0 = 0; q0 < L; q0 += 64) tiles.push_back(make_int4(s0 + q0, std::min(64, L - q0), s0, L));
-  }
-  if (tiles.empty()) return VR2_OK;
+  for (int i = 0; i < n_seq; ++i)
+    if (cu[i + 1] < cu[i]) return fail(VR2_ERR_ARG, "vr2_op_attention: cu_seqlens not monotone");
   cudaStream_t s = as_stream(stream_v);
-  int4* d = nullptr;
-  VR2_CUDA(cudaMalloc(&d, tiles.size() * 16));
-  cudaError_t e = cudaMemcpyAsync(d, tiles.data(), tiles.size() * 16, cudaMemcpyHostToDevice, s);
-  if (e == cudaSuccess)
-    e = attention_launch(static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(qkv_lo),
-                         static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(out_lo), d,
-                         static_cast<int>(tiles.size()), num_heads, 3 * num_heads * 80, num_heads * 80, s);
+  cudaError_t e = cudaSuccess;
+  void* d = nullptr;
+  if (qkv_lo == nullptr) {
+    // tcgen05 kernel: per-row segment bounds
+    const int n_rows = cu[n_seq] - cu[0];
+    if (cu[0] != 0) return fail(VR2_ERR_ARG, "vr2_op_attention: cu_seqlens must start at 0");
+    if (n_rows == 0) return VR2_OK;
+    std::vector<int2> seg(n_rows);
+    for (int i = 0; i < n_seq; ++i)
+      for (int r = cu[i]; r < cu[i + 1]; ++r) seg[r] = make_int2(cu[i], cu[i + 1]);
+    int dev = 0, sms = 148;
+    VR2_CUDA(cudaGetDevice(&dev));
+    VR2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    VR2_CUDA(cudaMalloc(&d, seg.size() * 8));
+    e = cudaMemcpyAsync(d, seg.data(), seg.size() * 8, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess)
+      e = attention_tc_launch(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out),
+                              static_cast<const int2*>(d), n_rows, num_heads, 3 * num_heads * 80, num_heads * 80, sms, s);
+  } else {
+    std::vector<int4> tiles;
+    for (int i = 0; i < n_seq; ++i) {
+      const int s0 = cu[i], L = cu[i + 1] - cu[i];
+      for (int q0 = 0; q0 < L; q0 += 64) tiles.push_back(make_int4(s0 + q0, std::min(64, L - q0), s0, L));
+    }
+    if (tiles.empty()) return VR2_OK;
+    VR2_CUDA(cudaMalloc(&d, tiles.size() * 16));
+    e = cudaMemcpyAsync(d, tiles.data(), tiles.size() * 16, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess)
+      e = attention_launch(static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(qkv_lo),
+                           static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(out_lo),
+                           static_cast<const int4*>(d), static_cast<int>(tiles.size()), num_heads, 3 * num_heads * 80,
+                           num_heads * 80, s);
+  }
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   cudaFree(d);
   if (e != cudaSuccess) return fail(VR2_ERR_CUDA, "vr2_op_attention: %s", cudaGetErrorString(e));
