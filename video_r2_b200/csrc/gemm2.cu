@@ -1,7 +1,7 @@
 // CTA-pair (tcgen05 cta_group::2) GEMM for the three GEMM shapes that carry 97 % of the tower's FLOPs:
 //
 //   EPI_QKV     C = xb * Wqkv^T      epilogue: * rstd(x), + bias, 2-D rotary on q,k, bf16           (N = 3840, BN = 240)
-//   EPI_RESID   C = A  * W^T         epilogue: x += C + bias (fp32), xb = bf16(x * w_norm), sum x^2  (N = 1280, BN = 160)
+//   EPI_RESID   C = A  * W^T         epilogue: x += C + bias (fp32), xb = bf16(x * w_norm), sum x^2  (N = 1280, BN = 256)
 //   EPI_SWIGLU  C = xb * Wgu^T       epilogue: * rstd, + bias, silu(gate) * up, bf16                 (N = 6912, BN = 256)
 //
 // Why a second kernel (ncu r01c, profiles/): in the single-CTA kernel (gemm.cu) the tensor core's operand reads
@@ -53,18 +53,22 @@ struct Cfg2<EPI_SWIGLU, 0> {
   static constexpr int out_bytes = 2 * 2 * 16384;  // double-buffered 128 x 128 bf16 as two 128B-swizzled 64-column boxes
   static constexpr int aux_bytes = 0;
 };
-// EPI_RESID moves its 128 x 160 tile through shared memory in four sub-steps of 40 columns, alternating between two
-// 30 KB buffers (fp32 residual: 2 boxes of 20 columns, updated in place; bf16 operand: 1 box of 40 columns), each
-// served by its own group of 8 epilogue warps: while one buffer is being computed on, the other one's stores drain
-// and its next residual piece loads.  Small buffers leave room for a 6-stage operand ring: the MMA main loop is
-// TMA-latency bound (ncu r01d: tensor pipe 29 % / 43 % with a 4-stage ring and whole-tile buffers).
-constexpr int kSubX = 2 * kBox;
-constexpr int kSubBytes = 3 * kBox;
+// EPI_RESID moves its 128 x 256 tile through shared memory in eight sub-steps of 32 columns over four 24 KB buffers
+// (fp32 residual: one [128 x 32] box with 128-byte rows, SWIZZLE_128B, updated in place; bf16 operand: one [128 x 32]
+// box with 64-byte rows, SWIZZLE_64B), each buffer served by its own group of 4 epilogue warps (one per TMEM lane
+// quarter): while one buffer is computed on, the others' stores drain and their next residual pieces load.
+// History (profiles/): whole-tile buffers with 128 x 160 tiles left a 4-stage ring of short stages and a serial
+// load -> compute -> store chain (tensor pipe 29 % / 43 %); 256-wide tiles keep the operand traffic per FLOP of the
+// gate|up GEMM, small buffers keep a 4-stage ring of 32 KB stages.
+constexpr int kSubX = 128 * 128;      // [128 rows x 32 fp32]
+constexpr int kSubXb = 128 * 64;      // [128 rows x 32 bf16]
+constexpr int kSubBytes = kSubX + kSubXb;
+constexpr int kResidBufs = 4;
 template <>
 struct Cfg2<EPI_RESID, 0> {
-  static constexpr int BN = 160, groups = 4, stages = 6;
-  static constexpr int out_bytes = 2 * kSubBytes;
-  static constexpr int aux_bytes = 4 * 128 * 4;          // per column group partial sums of squares
+  static constexpr int BN = 256, groups = 4, stages = 4;
+  static constexpr int out_bytes = kResidBufs * kSubBytes;
+  static constexpr int aux_bytes = 4 * 128 * 4;          // per warp group partial sums of squares
 };
 
 template <int EPI, int V>
@@ -104,10 +108,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint64_t* empty_bar = full_bar + C::stages;
   uint64_t* acc_full = empty_bar + C::stages;
   uint64_t* acc_empty = acc_full + 2;
-  uint64_t* store_ready = acc_empty + 2;  // [2] (one per residual half buffer; [0] otherwise)
-  uint64_t* out_free = store_ready + 2;   // [2]
-  uint64_t* aux_full = out_free + 2;      // [2] residual half tile / rotary tables landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + 2);
+  uint64_t* store_ready = acc_empty + 2;  // [4] (one per residual buffer; [0] otherwise)
+  uint64_t* out_free = store_ready + 4;   // [2]
+  uint64_t* aux_full = out_free + 2;      // [4] residual piece / rotary tables landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + 4);
   uint8_t* out_base = smem + L::out_off;
   uint8_t* aux_base = smem + L::aux_off;
 
@@ -143,7 +147,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], 2 * E);  // leader's: every epilogue warp of both CTAs
       mbar_init(&out_free[s], 1);
-      mbar_init(&store_ready[s], EPI == EPI_RESID ? E / 2 : E);
+    }
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&store_ready[s], EPI == EPI_RESID ? E / kResidBufs : E);
       mbar_init(&aux_full[s], 1);
     }
     fence_mbar_init();
@@ -211,42 +217,40 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ------------------------------------------------------------ store warp: everything the epilogue moves by TMA
     uint32_t local = 0;
     if constexpr (EPI == EPI_RESID) {
-      // Sub-step st = 4 * (tile ordinal) + k covers tile columns [40k, 40k + 40) and uses buffer k & 1.  Per buffer:
+      // Sub-step st = 8 * (tile ordinal) + k covers tile columns [32k, 32k + 32) and uses buffer k & 3.  Per buffer:
       //   load residual piece -> epilogue (in place) -> store x, xb -> stores have read the buffer -> load its next piece.
+      constexpr int NB = kResidBufs;
       float* red = reinterpret_cast<float*>(aux_base);
       const int n_local = tile_begin < tile_end ? (tile_end - tile_begin + tile_step - 1) / tile_step : 0;
-      const int n_sub = 4 * n_local;
+      const int n_sub = 8 * n_local;
       auto coords = [&](int st, int& m0, int& n0, int& n_blk) {
-        const int tile = tile_begin + (st >> 2) * tile_step;
+        const int tile = tile_begin + (st >> 3) * tile_step;
         m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
         n_blk = tile % num_n;
-        n0 = n_blk * BN + (st & 3) * 40;
+        n0 = n_blk * BN + (st & 7) * 32;
       };
-      auto load_x = [&](int st) {   // fp32 residual piece of sub-step st -> its buffer (2 boxes of 20 columns)
+      auto load_x = [&](int st) {   // fp32 residual piece of sub-step st -> its buffer
         int m0, n0, n_blk;
         coords(st, m0, n0, n_blk);
-        uint8_t* xb = out_base + (st & 1) * kSubBytes;
-        mbar_expect_tx(&aux_full[st & 1], kSubX);
-        tma_load_2d(xb, &tm0, &aux_full[st & 1], n0, m0);
-        tma_load_2d(xb + kBox, &tm0, &aux_full[st & 1], n0 + 20, m0);
+        mbar_expect_tx(&aux_full[st % NB], kSubX);
+        tma_load_2d(out_base + (st % NB) * kSubBytes, &tm0, &aux_full[st % NB], n0, m0);
       };
       if (lane == 0)
-        for (int st = 0; st < 2 && st < n_sub; ++st) load_x(st);
+        for (int st = 0; st < NB && st < n_sub; ++st) load_x(st);
       for (int st = 0; st < n_sub; ++st) {
         int m0, n0, n_blk;
         coords(st, m0, n0, n_blk);
-        const int b = st & 1;
-        mbar_wait(&store_ready[b], (st >> 1) & 1u);
+        const int b = st % NB;
+        mbar_wait(&store_ready[b], (st / NB) & 1u);
         if (lane == 0) {
           const uint8_t* xb = out_base + b * kSubBytes;
           tma_store_2d(&tm0, xb, n0, m0);
-          tma_store_2d(&tm0, xb + kBox, n0 + 20, m0);
           tma_store_2d(&tm1, xb + kSubX, n0, m0);
           tma_store_commit();
         }
-        if ((st & 3) == 3) {
-          // sum of squares of the new residual rows over this tile's 160 columns: one value per (row, column block),
-          // part-major [N/160][M] so producers and consumers both touch it coalesced; fixed order -> deterministic
+        if ((st & 7) == 7) {
+          // sum of squares of the new residual rows over this tile's 256 columns: one value per (row, column block),
+          // part-major [N/256][M] so producers and consumers both touch it coalesced; fixed order -> deterministic
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int row = lane + 32 * k;
@@ -255,9 +259,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           __syncwarp();
         }
-        if (lane == 0) {
-          tma_store_wait_read<0>();   // the stores have read the buffer: it may be refilled
-          if (st + 2 < n_sub) load_x(st + 2);
+        if (lane == 0 && st >= 1) {
+          // refill one sub-step behind: the previous sub-step's stores have had a whole epilogue step to drain
+          tma_store_wait_read<1>();
+          if (st - 1 + NB < n_sub) load_x(st - 1 + NB);
         }
       }
     } else if constexpr (EPI == EPI_QKV) {
@@ -320,25 +325,25 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const bool valid = r < p.M;
 
       if constexpr (EPI == EPI_RESID) {
-        // warp group g (8 warps) owns buffer g and the sub-steps k = g, g + 2 of every tile; inside a sub-step its two
-        // column halves c2 take 20 columns each (one fp32 box; half of the bf16 box)
+        // warp group g = cg (one warp per TMEM lane quarter) owns buffer g and the sub-steps k = g, g + 4 of every
+        // tile: 32 columns per sub-step, thread = row
         float* red = reinterpret_cast<float*>(aux_base);
-        const int g = cg >> 1, c2 = cg & 1;
+        const int g = cg;
         uint8_t* buf = out_base + g * kSubBytes;
-        float4* xrow = reinterpret_cast<float4*>(buf + c2 * kBox + row * 80);
-        uint2* xbrow = reinterpret_cast<uint2*>(buf + kSubX + row * 80 + c2 * 40);
+        uint8_t* xrow = buf + row * 128;               // 8 chunks of 16 bytes, chunk index XOR (row & 7)
+        uint8_t* xbrow = buf + kSubX + row * 64;        // 4 chunks of 16 bytes, chunk index XOR ((row >> 1) & 3)
+        const int sx = row & 7, sb = (row >> 1) & 3;
         float ss = 0.f;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-          const int col = (g + 2 * i) * 40 + c2 * 20;
+          const int col = (g + 4 * i) * 32;
           mbar_wait(&aux_full[g], (2 * local + i) & 1u);   // residual piece landed (the buffer's previous stores have drained)
           if (i == 0) {
             mbar_wait(&acc_full[as], use & 1u);
             tc_fence_after();
           }
-          uint32_t v[20];
-          tmem_ld16(taddr + col, v);
-          tmem_ld4(taddr + col + 16, v + 16);
+          uint32_t v[32];
+          tmem_ld32(taddr + col, v);
           tmem_ld_wait();
           if (i == 1) {   // all of this warp's TMEM reads of the tile are complete
             tc_fence_before();
@@ -347,9 +352,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               if (leader) mbar_arrive(&acc_empty[as]); else mbar_arrive_cluster(acc_empty_leader + as * 8);
             }
           }
+          uint32_t pk[16];
 #pragma unroll
-          for (int j = 0; j < 5; ++j) {
-            const float4 xo = xrow[j];
+          for (int j = 0; j < 8; ++j) {
+            float4* xp = reinterpret_cast<float4*>(xrow + ((j ^ sx) << 4));
+            const float4 xo = *xp;
             const float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col + 4 * j));
             const float4 w = __ldg(reinterpret_cast<const float4*>(p.norm_w + n0 + col + 4 * j));
             float4 f;
@@ -358,10 +365,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             f.z = __uint_as_float(v[4 * j + 2]) + bi.z + xo.z;
             f.w = __uint_as_float(v[4 * j + 3]) + bi.w + xo.w;
             ss = fmaf(f.x, f.x, ss); ss = fmaf(f.y, f.y, ss); ss = fmaf(f.z, f.z, ss); ss = fmaf(f.w, f.w, ss);
-            xrow[j] = f;                                                         // new residual, in place
-            xbrow[j] = make_uint2(pack_bf16x2(f.x * w.x, f.y * w.y), pack_bf16x2(f.z * w.z, f.w * w.w));  // next GEMM's operand
+            *xp = f;                                                         // new residual, in place
+            pk[2 * j] = pack_bf16x2(f.x * w.x, f.y * w.y);                   // next GEMM's operand: x * w_norm
+            pk[2 * j + 1] = pack_bf16x2(f.z * w.z, f.w * w.w);
           }
-          if (i == 1) red[cg * 128 + row] = ss;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(xbrow + ((j ^ sb) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+          if (i == 1) red[g * 128 + row] = ss;
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(&store_ready[g]);
@@ -509,8 +520,8 @@ cudaError_t launch2(const GemmArgs& a, int num_sms, cudaStream_t stream, const c
          encode(&tm1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.cos_tab, 40, a.M, 160, 20, BM, false) &&
          encode(&tm2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.sin_tab, 40, a.M, 160, 20, BM, false);
   } else if (EPI == EPI_RESID) {
-    ok = ok && encode(&tm0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.x, a.N, a.M, a.ldx * 4, 20, BM, false) &&
-         encode(&tm1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.out_bf16, a.N, a.M, a.ld_out * 2, 40, BM, false);
+    ok = ok && tma_encode_2d_swz(&tm0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a.x, a.N, a.M, a.ldx * 4, 32, BM, 128) &&
+         tma_encode_2d_swz(&tm1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.out_bf16, a.N, a.M, a.ld_out * 2, 32, BM, 64);
     tm2 = tm1;
   } else {
     ok = ok && encode(&tm0, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.out_bf16, a.N / 2, a.M, a.ld_out * 2, 64, BM, true);
@@ -558,13 +569,13 @@ bool gemm2_supports(const GemmArgs& a) {
   if (a.A_lo != nullptr || a.row_map != nullptr) return false;
   switch (a.epilogue) {
     case EPI_QKV: return a.N % 240 == 0 && (a.N / 3) % 80 == 0;
-    case EPI_RESID: return (a.flags & GEMM_ADD_RESID) != 0 && a.N % 160 == 0 && a.bias != nullptr;
+    case EPI_RESID: return (a.flags & GEMM_ADD_RESID) != 0 && a.N % 256 == 0 && a.bias != nullptr;
     case EPI_SWIGLU: return a.N % 256 == 0;
     default: return false;
   }
 }
 
-int gemm2_resid_parts(int n) { return n / 160; }
+int gemm2_resid_parts(int n) { return n / 256; }
 
 cudaError_t gemm2_launch(const GemmArgs& a, int num_sms, cudaStream_t stream, const char** err) {
   switch (a.epilogue) {
