@@ -49,8 +49,9 @@ struct Cfg2<EPI_QKV, 0> {
 };
 template <>
 struct Cfg2<EPI_SWIGLU, 0> {
-  static constexpr int BN = 256, groups = 4, stages = 5;
-  static constexpr int out_bytes = 2 * 2 * 16384;  // double-buffered 128 x 128 bf16 as two 128B-swizzled 64-column boxes
+  static constexpr int BN = 256, groups = 4, stages = 6;
+  static constexpr int out_bytes = 2 * 16384;  // 128 x 128 bf16 as two 128B-swizzled 64-column boxes (single buffer: its
+                                               // store drains long before the next tile's accumulator is complete)
   static constexpr int aux_bytes = 0;
 };
 // EPI_RESID moves its 128 x 256 tile through shared memory in eight sub-steps of 32 columns over four 24 KB buffers
@@ -294,14 +295,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
           const int n_blk = tile % num_n;
           mbar_wait(&store_ready[0], local & 1u);
-          const uint8_t* ob = out_base + (local & 1u) * 32768;
-          tma_store_2d(&tm0, ob, n_blk * (BN / 2), m0);
-          tma_store_2d(&tm0, ob + 16384, n_blk * (BN / 2) + 64, m0);
+          tma_store_2d(&tm0, out_base, n_blk * (BN / 2), m0);
+          tma_store_2d(&tm0, out_base + 16384, n_blk * (BN / 2) + 64, m0);
           tma_store_commit();
-          if (local >= 1) {
-            tma_store_wait_read<1>();            // the previous tile's store has read its buffer
-            mbar_arrive(&out_free[(local - 1) & 1u]);
-          }
+          tma_store_wait_read<0>();              // the store has read the buffer
+          mbar_arrive(&out_free[0]);
         }
       }
     }
@@ -454,11 +452,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int q = 0; q < p.ssq_parts; ++q) s += p.ssq_in[static_cast<int64_t>(q) * p.M + r];
           rstd = rsqrtf(s * p.inv_dim + p.eps);
         }
-        if (use > 0) mbar_wait(&out_free[as], (use - 1) & 1u);   // this buffer's previous store has drained
+        if (local > 0) mbar_wait(&out_free[0], (local - 1) & 1u);   // the previous tile's store has drained
         mbar_wait(&acc_full[as], use & 1u);
         tc_fence_after();
         // 128B-swizzled [128 x 64 bf16] boxes: 16-byte chunk index XOR (row & 7), as TMA SWIZZLE_128B expects
-        uint8_t* orow = out_base + as * 32768 + (cg >> 1) * 16384 + row * 128;
+        uint8_t* orow = out_base + (cg >> 1) * 16384 + row * 128;
 #pragma unroll
         for (int piece = 0; piece < 2; ++piece) {
           const int c = cg * 32 + piece * 16;
