@@ -1,0 +1,30 @@
+"""GPU: the host-to-host streaming helper returns exactly what the synchronous path returns."""
+import pytest
+import torch
+
+from oracle import tower as T
+
+pytestmark = pytest.mark.gpu
+
+
+def test_host_pipeline_matches_synchronous_path():
+    import video_r2_b200 as vr2
+    cfg_o = T.TowerConfig(depth=2, fullatt_block_indexes=(1,))
+    tower = vr2.VisionTower(vr2.VisionConfig(depth=2, fullatt_block_indexes=(1,)), T.make_weights(cfg_o, seed=2), device="cuda:0")
+    grids = [[[2, 8, 12]], [[1, 4, 6], [2, 6, 6]], [[2, 8, 12]], [[3, 10, 8]], [[2, 8, 12]]]
+    xs, ids = [], []
+    for k, g in enumerate(grids):
+        n = sum(t * h * w for t, h, w in g)
+        xs.append(torch.randn(n, 1176, generator=torch.Generator().manual_seed(k)).to(torch.bfloat16).pin_memory())
+        row = [5, 6, 151652] + [151656] * (g[0][0] * g[0][1] * g[0][2] // 4) + [151653, 7]
+        ids.append(torch.tensor([row], dtype=torch.int64).pin_memory())
+    pipe = vr2.HostPipeline(tower, depth=2)
+    for x, g, i in zip(xs, grids, ids):
+        pipe.submit(x, g, input_ids_host=i, video_grid_thw=torch.tensor(g[:1]), second_per_grid_ts=torch.tensor([1.5]))
+    got = pipe.drain()
+    assert len(got) == len(grids)
+    for (emb, pos), x, g, i in zip(got, xs, grids, ids):
+        ref = tower(x.cuda(), g)
+        rpos, _ = vr2.get_rope_index(i.cuda(), None, torch.tensor(g[:1]).cuda(), torch.tensor([1.5]).cuda(), None)
+        assert emb.dtype == torch.bfloat16 and torch.equal(emb, ref.cpu())
+        assert torch.equal(pos, rpos.cpu())

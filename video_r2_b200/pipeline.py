@@ -1,0 +1,108 @@
+"""Host-to-host streaming of the hot path: pinned host pixels (+ input_ids) in, pinned host embeddings
+(+ M-RoPE position ids) out, with the copies of neighbouring batches overlapped with the tower's kernels.
+
+Video-R2's callers hand `self.visual(...)` device tensors (the collator has already moved them), so the
+drop-in patch never copies.  An evaluation / rollout loop that feeds clips from host memory can use this
+instead of a synchronous `.to(device)` -> forward -> `.cpu()` per batch: three CUDA streams (H2D, compute, D2H)
+and `depth` device buffers per direction, ordered by events only — no host synchronisation inside `submit`.
+
+    pipe = vr2.HostPipeline(tower, depth=2)
+    for x_host, grid in batches:                 # x_host: pinned [N, 1176] bf16 / fp32
+        pipe.submit(x_host, grid, out_host=buf)  # returns immediately
+    for emb_host, pos_host in pipe.results():    # in submission order; blocks on that batch's D2H event only
+        ...
+"""
+from __future__ import annotations
+
+import collections
+
+import torch
+
+from .rope_index import get_rope_index
+
+
+class HostPipeline:
+    def __init__(self, tower, depth: int = 2, rope_config=None):
+        if depth < 1:
+            raise ValueError("depth must be >= 1")
+        self.tower = tower
+        self.dev = tower.device
+        self.depth = depth
+        self.rope_config = rope_config
+        self.s_in = torch.cuda.Stream(self.dev)
+        self.s_out = torch.cuda.Stream(self.dev)
+        self._in = [None] * depth          # device pixel buffers
+        self._ids = [None] * depth
+        self._out = [None] * depth         # device embedding buffers
+        self._compute_done = [None] * depth
+        self._d2h_done = [None] * depth
+        self._pending = collections.deque()
+        self._n = 0
+
+    def _buf(self, store, slot, shape, dtype):
+        b = store[slot]
+        if b is None or b.shape != tuple(shape) or b.dtype != dtype:
+            b = torch.empty(tuple(shape), dtype=dtype, device=self.dev)
+            store[slot] = b
+        return b
+
+    @torch.no_grad()
+    def submit(self, x_host: torch.Tensor, grid_thw, out_host: torch.Tensor = None, input_ids_host: torch.Tensor = None,
+               video_grid_thw=None, second_per_grid_ts=None, pos_host: torch.Tensor = None, out_dtype=None):
+        """Enqueue one batch.  `grid_thw` describes x_host's rows; when `input_ids_host` is given the M-RoPE position
+        ids of that batch are computed too (`video_grid_thw` / `second_per_grid_ts`: device or host tensors)."""
+        slot = self._n % self.depth
+        self._n += 1
+        cur = torch.cuda.current_stream(self.dev)
+        plan = self.tower.plan(grid_thw)
+        odt = out_dtype or (x_host.dtype if x_host.dtype in (torch.float32, torch.bfloat16) else torch.bfloat16)
+        # ---- H2D on the copy-in stream, after the compute that last read this slot
+        with torch.cuda.stream(self.s_in):
+            if self._compute_done[slot] is not None:
+                self.s_in.wait_event(self._compute_done[slot])
+            x_dev = self._buf(self._in, slot, x_host.shape, x_host.dtype)
+            x_dev.copy_(x_host, non_blocking=True)
+            ids_dev = None
+            if input_ids_host is not None:
+                ids_dev = self._buf(self._ids, slot, input_ids_host.shape, input_ids_host.dtype)
+                ids_dev.copy_(input_ids_host, non_blocking=True)
+            h2d = torch.cuda.Event()
+            h2d.record(self.s_in)
+        # ---- kernels on the caller's stream, after the H2D and after the D2H that last read this slot's output
+        cur.wait_event(h2d)
+        if self._d2h_done[slot] is not None:
+            cur.wait_event(self._d2h_done[slot])
+        out_dev = self._buf(self._out, slot, (plan.num_tokens, self.tower.cfg.out_hidden_size), odt)
+        self.tower.forward(x_dev, plan, out=out_dev)
+        pos_dev = None
+        if ids_dev is not None:
+            kw = {"config": self.rope_config} if self.rope_config is not None else {}
+            pos_dev, _ = get_rope_index(ids_dev, None, video_grid_thw, second_per_grid_ts, None, **kw)
+        done = torch.cuda.Event()
+        done.record(cur)
+        self._compute_done[slot] = done
+        # ---- D2H on the copy-out stream
+        if out_host is None:
+            out_host = torch.empty(out_dev.shape, dtype=out_dev.dtype).pin_memory()
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(done)
+            out_host.copy_(out_dev, non_blocking=True)
+            if pos_dev is not None:
+                if pos_host is None:
+                    pos_host = torch.empty(pos_dev.shape, dtype=pos_dev.dtype).pin_memory()
+                pos_host.copy_(pos_dev, non_blocking=True)
+                pos_dev.record_stream(self.s_out)
+            d2h = torch.cuda.Event()
+            d2h.record(self.s_out)
+        self._d2h_done[slot] = d2h
+        self._pending.append((d2h, out_host, pos_host))
+
+    def results(self):
+        """Yields (embeddings_host, position_ids_host or None) in submission order."""
+        while self._pending:
+            ev, out_host, pos_host = self._pending.popleft()
+            ev.synchronize()
+            yield out_host, pos_host
+
+    def drain(self):
+        return list(self.results())
