@@ -146,6 +146,15 @@ size_t vr2_tower_workspace_bytes(const vr2_tower* tower, int64_t n_patches);
  * vr2_tower_workspace_bytes() bytes, 1024-byte aligned. */
 int vr2_tower_forward(vr2_tower* tower, const vr2_plan* plan, const void* pixels_dev, int32_t pixels_dtype,
                       void* out_dev, int32_t out_dtype, void* workspace_dev, size_t workspace_bytes, void* stream);
+/* Same forward, with the caller's masked_scatter fused into the merger's last store: merged token k (original order)
+ * is written to out_dev[dest_rows_dev[k], 0:out_hidden] of a buffer with row pitch ld_out elements — e.g.
+ * inputs_embeds viewed as [B*S, hidden] with dest_rows = the flat positions of <|video_pad|> (vr2_token_positions).
+ * Replaces Video-R2 train/src/train/monkey_patch_forward.py:385-406 (masked_scatter of video_embeds) together with
+ * the tower call at :392; rows not named in dest_rows are left untouched. */
+int vr2_tower_forward_scatter(vr2_tower* tower, const vr2_plan* plan, const void* pixels_dev, int32_t pixels_dtype,
+                              void* out_dev, int32_t out_dtype, int64_t ld_out, const int32_t* dest_rows_dev,
+                              void* workspace_dev, size_t workspace_bytes, void* stream);
+
 /* Per-kernel-kind device timing.  vr2_tower_profile(mask) selects kinds (bit k = vr2_kernel_kind k; 0 turns it
  * off) and resets the counters; while selected, vr2_tower_forward brackets every launch of that kind with a
  * cudaEvent pair on the caller's stream.  vr2_tower_profile_read synchronises on those events and returns the
@@ -195,6 +204,21 @@ int vr2_rope_index(const vr2_rope_config* cfg, const int64_t* input_ids_dev, con
                    int32_t B, int32_t S, const int64_t* image_thw_dev, int32_t n_img, const int64_t* video_thw_dev,
                    int32_t n_vid, const float* second_per_grid_ts_dev, void* scratch_dev, int64_t* position_ids_dev,
                    int64_t* deltas_dev, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Placing visual tokens for the decoder (monkey_patch_forward.py:372-406).
+ * ---------------------------------------------------------------------- */
+/* positions_dev[k] = flat index of the k-th element of input_ids_dev[0:n] equal to token_id (k < capacity), i.e. the
+ * order in which `mask = input_ids == token_id; x.masked_scatter(mask[..., None], embeds)` consumes the rows of
+ * embeds.  *count_host = number of matches (may exceed capacity; HF raises "features and tokens do not match" when it
+ * differs from the number of features).  Synchronises `stream`.  scratch_dev: vr2_token_positions_scratch_bytes(n). */
+size_t vr2_token_positions_scratch_bytes(int64_t n);
+int vr2_token_positions(const int64_t* input_ids_dev, int64_t n, int64_t token_id, int32_t* positions_dev,
+                        int64_t capacity, void* scratch_dev, int64_t* count_host, void* stream);
+/* dst[dest_rows[k], 0:row_elems] = convert(src[k, 0:row_elems]) for k < n_rows; src rows contiguous, dst row pitch
+ * ld_dst elements; dtypes fp32 / bf16; row_elems and ld_dst multiples of 8.  The scatter for cached embeddings. */
+int vr2_scatter_rows(const void* src_dev, int32_t src_dtype, void* dst_dev, int32_t dst_dtype,
+                     const int32_t* dest_rows_dev, int64_t n_rows, int64_t row_elems, int64_t ld_dst, void* stream);
 
 /* ------------------------------------------------------------------------
  * Single operators, exported so tests can pin each kernel against the oracle.

@@ -8,11 +8,12 @@ own plugin mechanism (class-attribute patching of the Hugging Face model classes
 Everything heavy lives in libvr2.so (video_r2_b200/csrc, C ABI in include/vr2.h)."""
 from ._lib import LIB_PATH, Vr2Error, lib
 from .rope_index import RopeConfig, get_rope_index
+from .embed import embed_visual_tokens, scatter_rows, token_positions
 from .pipeline import HostPipeline
 from .tower import Plan, VisionConfig, VisionTower, gather_rows
 
 __all__ = ["LIB_PATH", "Vr2Error", "lib", "RopeConfig", "get_rope_index", "Plan", "VisionConfig", "VisionTower",
-           "gather_rows", "HostPipeline", "install", "uninstall", "refresh"]
+           "gather_rows", "HostPipeline", "embed_visual_tokens", "scatter_rows", "token_positions", "install", "uninstall", "refresh"]
 
 
 def install(*args, **kwargs):

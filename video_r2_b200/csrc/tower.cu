@@ -296,6 +296,7 @@ struct Workspace {
   __nv_bfloat16* hbuf;  // also the merger's hidden [N/4, 4h]
   float* ssq;
   __nv_bfloat16* pix;
+  int32_t* cmap;        // [N/4] merger store map composed with the caller's destination rows (forward_scatter)
   // VR2_PRECISION_SPLIT: rounding residuals of the buffers above (same layouts), else null
   __nv_bfloat16* xb_lo = nullptr;
   __nv_bfloat16* qkv_lo = nullptr;
@@ -318,6 +319,7 @@ Workspace carve_ws(const vr2_tower* t, int64_t n, void* base) {
   w.hbuf = reinterpret_cast<__nv_bfloat16*>(take(N * std::max<size_t>(t->ipad, h) * 2));
   w.ssq = reinterpret_cast<float*>(take(N * (h / 40) * 4));
   w.pix = reinterpret_cast<__nv_bfloat16*>(take(N * t->patch_k * 2));
+  w.cmap = reinterpret_cast<int32_t*>(take(N));   // N/4 tokens x 4 bytes
   if (t->precision == VR2_PRECISION_SPLIT) {
     w.xb_lo = reinterpret_cast<__nv_bfloat16*>(take(N * h * 2));
     w.qkv_lo = reinterpret_cast<__nv_bfloat16*>(take(N * 3 * h * 2));
@@ -341,9 +343,16 @@ extern "C" int64_t vr2_tower_launch_count(const vr2_tower* t, const vr2_plan* pl
   return (pixels_dtype == VR2_F32 ? 1 : 0) + 1 + 5 * static_cast<int64_t>(t->cfg.depth) + 3;  // memset is not a kernel
 }
 
-extern "C" int vr2_tower_forward(vr2_tower* t, const vr2_plan* plan, const void* pixels, int32_t pixels_dtype,
-                                 void* out, int32_t out_dtype, void* workspace, size_t workspace_bytes,
-                                 void* stream_v) {
+namespace vr2 {
+cudaError_t compose_map(const int32_t* out_map, const int32_t* dest_rows, int32_t* composed, int64_t n,
+                        cudaStream_t stream);
+}
+
+// dest_rows == nullptr: merged token k -> out[k, :] (row pitch out_hidden).  Otherwise token k -> out[dest_rows[k], :]
+// with row pitch ld_out: the masked_scatter of the caller fused into the merger's last store.
+static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pixels, int32_t pixels_dtype, void* out,
+                              int32_t out_dtype, const int32_t* dest_rows, int64_t ld_out, void* workspace,
+                              size_t workspace_bytes, void* stream_v) {
   if (t == nullptr || plan == nullptr || pixels == nullptr || out == nullptr || workspace == nullptr)
     return fail(VR2_ERR_ARG, "vr2_tower_forward: null argument");
   if (!t->finalized) return fail(VR2_ERR_STATE, "vr2_tower_forward: weights not finalized");
@@ -477,9 +486,29 @@ extern "C" int vr2_tower_forward(vr2_tower* t, const vr2_plan* plan, const void*
     a.out_bf16 = static_cast<__nv_bfloat16*>(out); a.out_f32 = static_cast<float*>(out);
     a.ld_out = t->cfg.out_hidden_size;
     a.row_map = plan->out_map;  // inverse window permute fused into the store (HF :512-513)
+    if (dest_rows != nullptr) {
+      VR2_CUDA(compose_map(plan->out_map, dest_rows, w.cmap, T, s));
+      a.row_map = w.cmap;
+      a.ld_out = ld_out;
+    }
     if ((rc = G(a, VR2_K_FC2, "merger.fc2")) != VR2_OK) return rc;
   }
   return VR2_OK;
+}
+
+extern "C" int vr2_tower_forward(vr2_tower* t, const vr2_plan* plan, const void* pixels, int32_t pixels_dtype,
+                                 void* out, int32_t out_dtype, void* workspace, size_t workspace_bytes,
+                                 void* stream_v) {
+  return tower_forward_impl(t, plan, pixels, pixels_dtype, out, out_dtype, nullptr, 0, workspace, workspace_bytes, stream_v);
+}
+
+extern "C" int vr2_tower_forward_scatter(vr2_tower* t, const vr2_plan* plan, const void* pixels, int32_t pixels_dtype,
+                                         void* out, int32_t out_dtype, int64_t ld_out, const int32_t* dest_rows_dev,
+                                         void* workspace, size_t workspace_bytes, void* stream_v) {
+  if (dest_rows_dev == nullptr) return fail(VR2_ERR_ARG, "vr2_tower_forward_scatter: null dest_rows");
+  if (t != nullptr && (ld_out < t->cfg.out_hidden_size || ld_out % 8 != 0))
+    return fail(VR2_ERR_ARG, "vr2_tower_forward_scatter: ld_out %lld must be >= out_hidden_size and a multiple of 8", (long long)ld_out);
+  return tower_forward_impl(t, plan, pixels, pixels_dtype, out, out_dtype, dest_rows_dev, ld_out, workspace, workspace_bytes, stream_v);
 }
 
 extern "C" int vr2_tower_set_precision(vr2_tower* t, int32_t precision) {

@@ -267,6 +267,34 @@ class VisionTower:
 
     __call__ = forward
 
+    @torch.no_grad()
+    def forward_into(self, hidden_states: torch.Tensor, grid_thw, dest: torch.Tensor, dest_rows: torch.Tensor):
+        """Tower forward whose merger stores merged token k at dest.view(-1, D)[dest_rows[k]] (dest's dtype): the
+        caller's masked_scatter fused into the last GEMM store (include/vr2.h vr2_tower_forward_scatter)."""
+        plan = self.plan(grid_thw)
+        x = hidden_states
+        if x.device != self.device:
+            x = x.to(self.device, non_blocking=True)
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.to(torch.bfloat16)
+        x = x.contiguous()
+        if x.dim() != 2 or x.shape[1] != self.cfg.patch_dim or x.shape[0] != plan.num_patches:
+            raise ValueError(f"hidden_states must be [{plan.num_patches}, {self.cfg.patch_dim}], got {tuple(x.shape)}")
+        if dest.device != self.device or not dest.is_contiguous() or dest.shape[-1] < self.cfg.out_hidden_size:
+            raise ValueError("dest must be a contiguous tensor on the tower's device with rows of >= out_hidden_size")
+        rows = dest_rows.to(device=self.device, dtype=torch.int32).contiguous()
+        if rows.numel() != plan.num_tokens:
+            raise ValueError(f"dest_rows has {rows.numel()} entries for {plan.num_tokens} visual tokens")
+        ws = self._workspace(plan.num_patches)
+        base = ws.data_ptr()
+        aligned = (base + 1023) & ~1023
+        with torch.cuda.device(self.device):
+            check(lib().vr2_tower_forward_scatter(self._h, plan._h, x.data_ptr(), _dtype_code(x.dtype), dest.data_ptr(),
+                                                  _dtype_code(dest.dtype), dest.shape[-1], rows.data_ptr(), aligned,
+                                                  ws.numel() - (aligned - base), _stream_ptr(self.device)),
+                  "vr2_tower_forward_scatter")
+        return dest
+
     KERNEL_KINDS = ("cast", "patch_embed", "qkv", "attn_window", "attn_full", "proj", "gate_up", "down",
                     "merger_norm", "fc1", "fc2")
 
