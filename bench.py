@@ -358,6 +358,34 @@ def run_vr2(args, rank, local_rank, world):
         tower.set_precision(args.precision)
         del fast_out, split_out
 
+    # ---- SURVEY §8f rank 1 (the caller side): tower + masked_scatter into inputs_embeds, fused vs the reference's way
+    widening = None
+    if world == 1:
+        emb = torch.zeros((1, len(row), cfg.out_hidden_size), dtype=torch.bfloat16, device=dev)
+        vmask = (ids_dev[:1] == 151656).unsqueeze(-1).expand_as(emb)
+
+        def ref_way(i):   # monkey_patch_forward.py:392-406 with the tower already replaced
+            feats = tower(pix_dev[i % n_rot], my_grid)
+            n_tok = (ids_dev[:1] == 151656).sum().item()
+            assert n_tok == feats.shape[0]
+            return emb.masked_scatter(vmask, feats)
+
+        def fused_way(i):
+            return vr2.embed_visual_tokens(tower, emb, ids_dev[:1], 151656, pix_dev[i % n_rot], my_grid)
+
+        for fn in (ref_way, fused_way):
+            for i in range(2):
+                fn(i)
+        # alternate the two (the step is power-capped: whatever runs later in a long burst runs at a lower clock)
+        t_ref, t_fused = [], []
+        for _ in range(3):
+            t_fused.append(timed(fused_way, args.steps) / args.steps)
+            t_ref.append(timed(ref_way, args.steps) / args.steps)
+        ms_ref, ms_fused = statistics.median(t_ref), statistics.median(t_fused)
+        same = torch.equal(ref_way(0), fused_way(0).clone())
+        widening = {"what": "tower + placement of the visual tokens in inputs_embeds [1, %d, %d] bf16" % (len(row), cfg.out_hidden_size),
+                    "forward_then_masked_scatter_ms": ms_ref, "fused_scatter_ms": ms_fused, "bit_identical": bool(same)}
+
     peaks, peak_src = _peaks()
     gu_ms, gu_n = prof.get("gate_up", (0.0, 0))
     gu_avg = gu_ms / max(1, gu_n)
@@ -400,6 +428,8 @@ def run_vr2(args, rank, local_rank, world):
     }
     if precise is not None:
         line["precise"] = precise
+    if widening is not None:
+        line["widening"] = widening
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             kind, run = cpu_reference_runner()

@@ -150,7 +150,8 @@ int vr2_tower_forward(vr2_tower* tower, const vr2_plan* plan, const void* pixels
  * is written to out_dev[dest_rows_dev[k], 0:out_hidden] of a buffer with row pitch ld_out elements — e.g.
  * inputs_embeds viewed as [B*S, hidden] with dest_rows = the flat positions of <|video_pad|> (vr2_token_positions).
  * Replaces Video-R2 train/src/train/monkey_patch_forward.py:385-406 (masked_scatter of video_embeds) together with
- * the tower call at :392; rows not named in dest_rows are left untouched. */
+ * the tower call at :392; rows not named in dest_rows are left untouched, tokens whose dest_rows entry is negative
+ * are not stored. */
 int vr2_tower_forward_scatter(vr2_tower* tower, const vr2_plan* plan, const void* pixels_dev, int32_t pixels_dtype,
                               void* out_dev, int32_t out_dtype, int64_t ld_out, const int32_t* dest_rows_dev,
                               void* workspace_dev, size_t workspace_bytes, void* stream);
@@ -210,11 +211,15 @@ int vr2_rope_index(const vr2_rope_config* cfg, const int64_t* input_ids_dev, con
  * ---------------------------------------------------------------------- */
 /* positions_dev[k] = flat index of the k-th element of input_ids_dev[0:n] equal to token_id (k < capacity), i.e. the
  * order in which `mask = input_ids == token_id; x.masked_scatter(mask[..., None], embeds)` consumes the rows of
- * embeds.  *count_host = number of matches (may exceed capacity; HF raises "features and tokens do not match" when it
- * differs from the number of features).  Synchronises `stream`.  scratch_dev: vr2_token_positions_scratch_bytes(n). */
+ * embeds; entries past the number of matches are -1 (consumers skip them).  The number of matches (may exceed
+ * capacity; HF raises "features and tokens do not match" when it differs from the number of features) is returned
+ * in *count_host, which synchronises `stream` — or pass count_host = NULL to stay asynchronous and fetch it later
+ * with vr2_token_positions_count(scratch_dev, n, ...), e.g. after the tower has been enqueued.
+ * scratch_dev: vr2_token_positions_scratch_bytes(n). */
 size_t vr2_token_positions_scratch_bytes(int64_t n);
 int vr2_token_positions(const int64_t* input_ids_dev, int64_t n, int64_t token_id, int32_t* positions_dev,
                         int64_t capacity, void* scratch_dev, int64_t* count_host, void* stream);
+int vr2_token_positions_count(const void* scratch_dev, int64_t n, int64_t* count_host, void* stream);
 /* dst[dest_rows[k], 0:row_elems] = convert(src[k, 0:row_elems]) for k < n_rows; src rows contiguous, dst row pitch
  * ld_dst elements; dtypes fp32 / bf16; row_elems and ld_dst multiples of 8.  The scatter for cached embeddings. */
 int vr2_scatter_rows(const void* src_dev, int32_t src_dtype, void* dst_dev, int32_t dst_dtype,

@@ -65,3 +65,21 @@ def test_tower_forward_with_fused_scatter_equals_forward_then_masked_scatter():
         assert torch.equal(out, ref)
     with pytest.raises(ValueError, match="features and video tokens do not match"):
         vr2.embed_visual_tokens(tower, emb.clone(), ids.cuda()[:, :-50], VID, x, grid)
+
+
+def test_embedding_reuse_is_keyed_on_tensor_identity_and_version():
+    import video_r2_b200 as vr2
+    cfg_o = T.TowerConfig(depth=1, fullatt_block_indexes=(0,))
+    tower = vr2.VisionTower(vr2.VisionConfig(depth=1, fullatt_block_indexes=(0,)), T.make_weights(cfg_o, seed=8), device="cuda:0")
+    grid = [[2, 8, 12]]
+    x = torch.randn(192, 1176, generator=torch.Generator().manual_seed(9)).to(torch.bfloat16).cuda()
+    a = tower(x, grid, reuse=2)
+    b = tower(x, grid, reuse=2)
+    assert b is a and tower.reuse_hits == 1              # same object, unmodified: served from the cache
+    y = x.clone()
+    c = tower(y, grid, reuse=2)
+    assert c is not a and torch.equal(c, a)              # equal content, different tensor: recomputed
+    x.mul_(2)                                            # in-place change bumps _version: no stale hit
+    d = tower(x, grid, reuse=2)
+    assert d is not a and not torch.equal(d, a) and tower.reuse_hits == 1
+    assert torch.equal(tower(x, grid), d)                # and the uncached path agrees

@@ -329,6 +329,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if constexpr (EPI == EPI_STORE) {
         const bool direct = p.row_map != nullptr;   // scattered rows (inverse window permute): row-per-thread stores
         const int64_t dest = valid ? (direct ? p.row_map[r] : r) : 0;
+        const bool store_row = valid && dest >= 0;   // a negative destination = "no place for this token" (scatter)
 #pragma unroll 1
         for (int c = cg * GC; c < (cg + 1) * GC; c += 16) {
           if (n0 + c >= p.N) break;        // N % 32 == 0 is checked on the host
@@ -351,7 +352,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           if (p.flags & GEMM_OUT_F32) {
             if (direct) {
-              if (valid) {
+              if (store_row) {
                 float* o = p.out_f32 + dest * p.ld_out + n0 + c;
 #pragma unroll
                 for (int j = 0; j < 16; j += 4)
@@ -367,7 +368,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           } else {
             const int64_t off = n0 + c;
             if (direct) {
-              if (valid) emit_row<SPLIT>(f, p.out_bf16 + dest * p.ld_out + off, p.out_lo ? p.out_lo + dest * p.ld_out + off : nullptr);
+              if (store_row) emit_row<SPLIT>(f, p.out_bf16 + dest * p.ld_out + off, p.out_lo ? p.out_lo + dest * p.ld_out + off : nullptr);
             } else if (SPLIT && p.out_lo == nullptr) {
               emit_piece<false>(st, f, p.out_bf16 + static_cast<int64_t>(row0) * p.ld_out + off, nullptr, p.ld_out, rows_valid, lane, 16);
             } else {

@@ -103,8 +103,10 @@ __global__ void scatter_rows_kernel(const Src* __restrict__ src, Dst* __restrict
        e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t row = e / vec_per_row;
     const int64_t v = e - row * vec_per_row;
+    const int32_t dr = dest_rows[row];
+    if (dr < 0) continue;   // no destination (fewer matches than rows): skipped, the caller reports the mismatch
     const Src* s = src + row * row_elems + v * 8;
-    Dst* d = dst + static_cast<int64_t>(dest_rows[row]) * ld_dst + v * 8;
+    Dst* d = dst + static_cast<int64_t>(dr) * ld_dst + v * 8;
     float f[8];
     if constexpr (sizeof(Src) == 2) {
       const uint4 u = __ldg(reinterpret_cast<const uint4*>(s));
@@ -155,21 +157,34 @@ extern "C" size_t vr2_token_positions_scratch_bytes(int64_t n) {
 
 extern "C" int vr2_token_positions(const int64_t* input_ids_dev, int64_t n, int64_t token_id, int32_t* positions_dev,
                                    int64_t capacity, void* scratch_dev, int64_t* count_host, void* stream_v) {
-  if (input_ids_dev == nullptr || n < 0 || (capacity > 0 && positions_dev == nullptr) || count_host == nullptr)
+  if (input_ids_dev == nullptr || n < 0 || (capacity > 0 && positions_dev == nullptr))
     return fail(VR2_ERR_ARG, "vr2_token_positions: null pointer");
   if (n > INT32_MAX) return fail(VR2_ERR_ARG, "vr2_token_positions: %lld elements exceed int32 row indexing", (long long)n);
-  *count_host = 0;
+  if (count_host != nullptr) *count_host = 0;
+  cudaStream_t s = as_stream(stream_v);
+  // entries past the number of matches stay -1: a consumer (vr2_tower_forward_scatter, vr2_scatter_rows) skips them
+  if (capacity > 0) VR2_CUDA(cudaMemsetAsync(positions_dev, 0xFF, static_cast<size_t>(capacity) * 4, s));
   if (n == 0) return VR2_OK;
   if (scratch_dev == nullptr) return fail(VR2_ERR_ARG, "vr2_token_positions: null scratch");
-  cudaStream_t s = as_stream(stream_v);
   const int blocks = static_cast<int>((n + kScanBlock - 1) / kScanBlock);
   int* counts = static_cast<int*>(scratch_dev);
   count_kernel<<<blocks, kScanBlock, 0, s>>>(input_ids_dev, n, token_id, counts);
   scan_counts_kernel<<<1, kScanBlock, 0, s>>>(counts, blocks);
   positions_kernel<<<blocks, kScanBlock, 0, s>>>(input_ids_dev, n, token_id, counts, positions_dev, capacity);
   VR2_CUDA(cudaGetLastError());
+  if (count_host != nullptr) return vr2_token_positions_count(scratch_dev, n, count_host, stream_v);
+  return VR2_OK;
+}
+
+extern "C" int vr2_token_positions_count(const void* scratch_dev, int64_t n, int64_t* count_host, void* stream_v) {
+  if (count_host == nullptr) return fail(VR2_ERR_ARG, "vr2_token_positions_count: null pointer");
+  *count_host = 0;
+  if (n <= 0) return VR2_OK;
+  if (scratch_dev == nullptr) return fail(VR2_ERR_ARG, "vr2_token_positions_count: null scratch");
+  cudaStream_t s = as_stream(stream_v);
+  const int64_t blocks = (n + kScanBlock - 1) / kScanBlock;
   int total = 0;
-  VR2_CUDA(cudaMemcpyAsync(&total, counts + blocks, 4, cudaMemcpyDeviceToHost, s));
+  VR2_CUDA(cudaMemcpyAsync(&total, static_cast<const int*>(scratch_dev) + blocks, 4, cudaMemcpyDeviceToHost, s));
   VR2_CUDA(cudaStreamSynchronize(s));   // the caller compares the count with the number of features (ValueError in HF)
   *count_host = total;
   return VR2_OK;

@@ -22,9 +22,24 @@ from ._lib import check, lib
 from .tower import _dtype_code, _stream_ptr
 
 
-def token_positions(input_ids: torch.Tensor, token_id: int, capacity: int = None):
-    """-> (positions int32 [min(count, capacity)] on input_ids' device, count).  positions[k] is the flat index (over
-    the contiguous [B, S] ids) of the k-th occurrence of token_id — the order masked_scatter consumes rows in."""
+class _Positions:
+    """Result of an asynchronous token_positions: `rows` (int32, -1 past the matches) is valid in stream order;
+    `count()` synchronises."""
+
+    def __init__(self, rows, scratch, n):
+        self.rows, self._scratch, self._n, self._count = rows, scratch, n, None
+
+    def count(self) -> int:
+        if self._count is None:
+            c = C.c_int64(0)
+            with torch.cuda.device(self.rows.device):
+                check(lib().vr2_token_positions_count(self._scratch.data_ptr(), self._n, C.byref(c),
+                                                      _stream_ptr(self.rows.device)), "vr2_token_positions_count")
+            self._count = c.value
+        return self._count
+
+
+def token_positions_async(input_ids: torch.Tensor, token_id: int, capacity: int = None) -> _Positions:
     if not input_ids.is_cuda:
         raise ValueError("token_positions: input_ids must be a CUDA tensor (no CPU path)")
     ids = input_ids.to(torch.int64).contiguous()
@@ -32,11 +47,18 @@ def token_positions(input_ids: torch.Tensor, token_id: int, capacity: int = None
     cap = n if capacity is None else int(capacity)
     pos = torch.empty(max(cap, 1), dtype=torch.int32, device=ids.device)
     scratch = torch.empty(max(lib().vr2_token_positions_scratch_bytes(n), 4), dtype=torch.uint8, device=ids.device)
-    count = C.c_int64(0)
     with torch.cuda.device(ids.device):
         check(lib().vr2_token_positions(ids.data_ptr(), n, int(token_id), pos.data_ptr(), cap, scratch.data_ptr(),
-                                        C.byref(count), _stream_ptr(ids.device)), "vr2_token_positions")
-    return pos[: min(count.value, cap)], count.value
+                                        None, _stream_ptr(ids.device)), "vr2_token_positions")
+    return _Positions(pos[:cap], scratch, n)
+
+
+def token_positions(input_ids: torch.Tensor, token_id: int, capacity: int = None):
+    """-> (positions int32 [min(count, capacity)] on input_ids' device, count).  positions[k] is the flat index (over
+    the contiguous [B, S] ids) of the k-th occurrence of token_id — the order masked_scatter consumes rows in."""
+    p = token_positions_async(input_ids, token_id, capacity)
+    count = p.count()
+    return p.rows[: min(count, p.rows.numel())], count
 
 
 def scatter_rows(src: torch.Tensor, dst: torch.Tensor, dest_rows: torch.Tensor) -> torch.Tensor:
@@ -65,8 +87,11 @@ def embed_visual_tokens(tower, inputs_embeds: torch.Tensor, input_ids: torch.Ten
     if not inputs_embeds.is_contiguous() or inputs_embeds.shape[-1] != tower.cfg.out_hidden_size:
         raise ValueError("embed_visual_tokens: inputs_embeds must be contiguous [..., out_hidden_size]")
     plan = tower.plan(grid_thw)
-    rows, count = token_positions(input_ids, token_id, capacity=plan.num_tokens)
+    pos = token_positions_async(input_ids, token_id, capacity=plan.num_tokens)
+    # the tower is enqueued before the host learns the count (the reference's `.sum().item()` also waits for the GPU,
+    # but with nothing queued behind it); destinations that do not exist are -1 and are skipped by the store
+    tower.forward_into(pixel_values, plan, inputs_embeds, pos.rows)
+    count = pos.count()
     if count != plan.num_tokens:
         raise ValueError(f"{what} features and {what.lower()} tokens do not match: tokens: {count}, features {plan.num_tokens}")
-    tower.forward_into(pixel_values, plan, inputs_embeds, rows)
     return inputs_embeds

@@ -26,6 +26,7 @@ from .rope_index import RopeConfig, get_rope_index
 from .tower import VisionConfig, VisionTower
 
 _ORIGINALS = {}
+_REUSE = 0   # install(reuse_embeddings=n): keep the last n tower outputs per module (see VisionTower.forward)
 
 
 def _tower_of(module) -> VisionTower:
@@ -49,7 +50,7 @@ def _transformers_major() -> int:
 
 
 def _visual_forward(self, hidden_states: torch.Tensor, grid_thw: torch.Tensor, **kwargs):
-    out = _tower_of(self).forward(hidden_states, grid_thw)
+    out = _tower_of(self).forward(hidden_states, grid_thw, reuse=_REUSE)
     if _transformers_major() >= 5:
         from transformers.modeling_outputs import BaseModelOutputWithPooling
         return BaseModelOutputWithPooling(last_hidden_state=None, pooler_output=out)
@@ -80,10 +81,14 @@ def _rope_5x(self, input_ids=None, mm_token_type_ids=None, image_grid_thw=None, 
                           config=_rope_cfg(self))
 
 
-def install(visual: bool = True, rope_index: bool = True):
-    """Patch the Hugging Face classes in place.  Idempotent."""
+def install(visual: bool = True, rope_index: bool = True, reuse_embeddings: int = 0):
+    """Patch the Hugging Face classes in place.  Idempotent.  reuse_embeddings=n keeps the last n tower outputs and
+    returns them when the same (unmodified) pixel tensor object is encoded again — GRPO encodes each clip three times
+    per step with a frozen tower; off by default because the returned tensor is then shared between calls."""
     from transformers.models.qwen2_5_vl import modeling_qwen2_5_vl as M
     from . import lib
+    global _REUSE
+    _REUSE = int(reuse_embeddings)
     lib()  # fail now, loudly, if libvr2.so is missing
     if visual and "visual" not in _ORIGINALS:
         cls = M.Qwen2_5_VisionTransformerPretrainedModel

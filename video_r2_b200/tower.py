@@ -12,6 +12,7 @@ import collections
 import ctypes as C
 import dataclasses
 import os
+import weakref
 
 import torch
 
@@ -179,6 +180,8 @@ class VisionTower:
         self._plans = collections.OrderedDict()
         self._plan_cache = plan_cache
         self._ws = None
+        self._emb_cache = collections.OrderedDict()   # embedding reuse, see forward(reuse=...)
+        self.reuse_hits = 0
         self.set_precision(precision or os.environ.get("VR2_PRECISION", "bf16"))
         self.load_state_dict(state_dict)
 
@@ -188,6 +191,7 @@ class VisionTower:
         check(lib().vr2_tower_set_precision(self._h, _lib.PRECISIONS[precision]), "vr2_tower_set_precision")
         self.precision = precision
         self._ws = None
+        self._emb_cache.clear()
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -240,9 +244,27 @@ class VisionTower:
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
-    def forward(self, hidden_states: torch.Tensor, grid_thw, out_dtype=None, out=None) -> torch.Tensor:
-        """hidden_states: [N, 1176] fp32/bf16 on this tower's device.  Returns [N/4, out_hidden]."""
+    def forward(self, hidden_states: torch.Tensor, grid_thw, out_dtype=None, out=None, reuse: int = 0) -> torch.Tensor:
+        """hidden_states: [N, 1176] fp32/bf16 on this tower's device.  Returns [N/4, out_hidden].
+
+        reuse > 0 keeps the last `reuse` results and returns the cached tensor when the SAME tensor object, unmodified
+        (same `_version`), is encoded again with the same grid — a frozen tower encodes one clip several times per
+        GRPO step (grpo_trainer.py:667-679 generate, :783 policy and :826-833 reference log-probs).  Identity, not
+        content, is the key, so a recycled address can never alias another clip; callers must treat the returned
+        tensor as read-only (the reference only reads it: monkey_patch_forward.py:400-406)."""
         plan = self.plan(grid_thw)
+        if reuse > 0 and out is None:
+            key = (id(hidden_states), plan.grid, out_dtype)
+            hit = self._emb_cache.get(key)
+            if hit is not None and hit[0]() is hidden_states and hit[1] == hidden_states._version:
+                self._emb_cache.move_to_end(key)
+                self.reuse_hits += 1
+                return hit[2]
+            result = self.forward(hidden_states, plan, out_dtype=out_dtype)
+            self._emb_cache[key] = (weakref.ref(hidden_states), hidden_states._version, result)
+            while len(self._emb_cache) > reuse:
+                self._emb_cache.popitem(last=False)
+            return result
         x = hidden_states
         if x.device != self.device:
             x = x.to(self.device, non_blocking=True)
