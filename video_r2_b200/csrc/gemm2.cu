@@ -337,7 +337,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const int col = (g + 4 * i) * 32;
           mbar_wait(&aux_full[g], (2 * local + i) & 1u);   // residual piece landed (the buffer's previous stores have drained)
           if (i == 0) {
-            mbar_wait(&acc_full[as], use & 1u);
+            mbar_wait_relaxed(&acc_full[as], use & 1u);
             tc_fence_after();
           }
           uint32_t v[32];
@@ -390,7 +390,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           ++aux_loads;
         }
         if (local > 0) mbar_wait(&out_free[0], (local - 1) & 1u);   // the previous tile's stores have drained
-        mbar_wait(&acc_full[as], use & 1u);
+        mbar_wait_relaxed(&acc_full[as], use & 1u);
         tc_fence_after();
         const uint8_t* cs_row = aux_base + row * 80;
         uint8_t* out_row = out_base + (cg * 2) * kBox + row * 80;
@@ -453,7 +453,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           rstd = rsqrtf(s * p.inv_dim + p.eps);
         }
         if (local > 0) mbar_wait(&out_free[0], (local - 1) & 1u);   // the previous tile's store has drained
-        mbar_wait(&acc_full[as], use & 1u);
+        mbar_wait_relaxed(&acc_full[as], use & 1u);
         tc_fence_after();
         // 128B-swizzled [128 x 64 bf16] boxes: 16-byte chunk index XOR (row & 7), as TMA SWIZZLE_128B expects
         uint8_t* orow = out_base + (cg >> 1) * 16384 + row * 128;
