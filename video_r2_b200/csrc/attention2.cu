@@ -8,15 +8,18 @@
 // key/value blocks that cover [lo of its first row, hi of its last row) and each row masks what is outside its own
 // segment.  With 64-patch windows a tile is exactly two windows and one key block.
 //
-// Persistent CTAs, 6 warps:
-//   warp 4 (one lane)  TMA producer: Q once per item, K|V blocks into a 3-stage ring.  A 128 x 80 operand tile is
-//                      two boxes: 64 columns (128-byte swizzle) + 16 columns (32-byte swizzle).
-//   warp 5 (one lane)  tcgen05.mma issuer:  S_j = Q K_j^T (5 MMAs of 128x128x16 into one of two TMEM S buffers),
-//                      O_j = P_j V_j (8 k-steps x {N=64, N=16}, V as an MN-major operand, fresh accumulator per block)
-//   warps 0-3          softmax, thread = query row = TMEM lane: row max, exp2, P_j -> shared memory (bf16, the
-//                      K-major 128B-swizzled layout the MMA reads), running max / sum; the block outputs O_j are
-//                      folded into 80 fp32 registers per row with the usual rescale, one block behind the MMAs so
-//                      the softmax of block j+1 overlaps P_j V_j.  Result -> shared memory -> one TMA store.
+// Persistent CTAs, 10 warps, TWO items in flight per CTA (streams 0 and 1, each with its own Q tile, S and O
+// accumulators in TMEM, P buffer and softmax warpgroup): while one stream's softmax warps work on their scores the
+// tensor core runs the other stream's MMAs, and the loads / stores of one item hide behind the other's compute.
+//   warp 8 (one lane)  TMA producer: Q per item, K|V blocks of both streams into one 3-stage ring, in the fixed
+//                      (stream, block) order the MMA issuer consumes them.  A 128 x 80 operand tile is two boxes:
+//                      64 columns (128-byte swizzle) + 16 columns (32-byte swizzle).
+//   warp 9 (one lane)  tcgen05.mma issuer:  S = Q K_j^T (5 MMAs of 128x128x16),  O_j = P_j V_j (8 k-steps x
+//                      {N=64, N=16}, V as an MN-major operand, fresh accumulator per block)
+//   warps 4x..4x+3     softmax of stream x, thread = query row = TMEM lane: row max, exp2, P_j -> shared memory
+//                      (bf16, the K-major 128B-swizzled layout the MMA reads), running max / sum; the block outputs
+//                      O_j are folded into 80 fp32 registers per row with the usual rescale.  Result -> shared
+//                      memory (aliasing the stream's P buffer) -> one TMA store.
 // fp32 scores, softmax and accumulation; bf16 operands (P is rounded to bf16 like q, k, v).
 #include "attention.cuh"
 
@@ -41,18 +44,18 @@ constexpr int Q16_BYTES = TQ * 32;           // [128 x 16 bf16], SWIZZLE_32B
 constexpr int TILE_BYTES = Q64_BYTES + Q16_BYTES;     // 20 KB: one 128 x 80 operand tile
 constexpr int KV_STAGE_BYTES = 2 * TILE_BYTES;        // K tile | V tile
 constexpr int P_BYTES = 2 * TQ * 128;                 // [128 x 128 bf16] as two 64-column SWIZZLE_128B atoms
-constexpr int OUT_BYTES = 2 * TQ * 80;                // two [128 x 40 bf16] boxes, 80-byte rows
+// the output staging of a stream (two [128 x 40 bf16] boxes, 80-byte rows = 20 KB) aliases its P buffer: P is dead
+// once the item's last P V has retired
 
-constexpr int OFF_Q = 0;
-constexpr int OFF_KV = OFF_Q + TILE_BYTES;
-constexpr int OFF_P = OFF_KV + KV_STAGES * KV_STAGE_BYTES;
-constexpr int OFF_OUT = OFF_P + 2 * P_BYTES;
-constexpr int OFF_BAR = OFF_OUT + OUT_BYTES;
+constexpr int OFF_Q = 0;                               // [2 streams]
+constexpr int OFF_KV = OFF_Q + 2 * TILE_BYTES;
+constexpr int OFF_P = OFF_KV + KV_STAGES * KV_STAGE_BYTES;   // [2 streams]
+constexpr int OFF_BAR = OFF_P + 2 * P_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 256;
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB shared-memory limit");
 
-constexpr int TM_S = 0;      // two S buffers: columns [0,128), [128,256)
-constexpr int TM_O = 256;    // two O buffers: columns [256,336), [384,464)
+constexpr int TM_S = 0;      // S of stream x: columns [128 x, 128 x + 128)
+constexpr int TM_O = 256;    // O of stream x: columns [256 + 128 x, +80)
 constexpr int TM_O_STRIDE = 128;
 
 // K-major operand tile with 32-byte rows (16 bf16 = one MMA k-step), SWIZZLE_32B: 8-row groups every 256 bytes
@@ -100,16 +103,18 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-__global__ void __launch_bounds__(192, 1)
+constexpr int kThreads = 320;   // 2 softmax warpgroups (one per stream) + producer warp + MMA warp
+
+__global__ void __launch_bounds__(kThreads, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUtensorMap tm16,
                const __grid_constant__ CUtensorMap tmOut, const int2* __restrict__ seg, int n_rows, int num_heads,
                int hidden, float scale_log2) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
 
-  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-  uint64_t* q_empty = q_full + 1;
-  uint64_t* kv_full = q_empty + 1;          // [KV_STAGES]
+  uint64_t* q_full = reinterpret_cast<uint64_t*>(smem + OFF_BAR);   // [2]
+  uint64_t* q_empty = q_full + 2;           // [2]
+  uint64_t* kv_full = q_empty + 2;          // [KV_STAGES]
   uint64_t* kv_empty = kv_full + KV_STAGES; // [KV_STAGES]
   uint64_t* s_full = kv_empty + KV_STAGES;  // [2]
   uint64_t* p_ready = s_full + 2;           // [2]
@@ -121,24 +126,24 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
   const int n_tiles = (n_rows + TQ - 1) / TQ;
   const int n_items = n_tiles * num_heads;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tm64);
     tma_prefetch_desc(&tm16);
     tma_prefetch_desc(&tmOut);
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
     for (int s = 0; s < KV_STAGES; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
+      mbar_init(&q_full[s], 1);
+      mbar_init(&q_empty[s], 1);
       mbar_init(&s_full[s], 1);
-      mbar_init(&p_ready[s], 4);   // one arrive per softmax warp
+      mbar_init(&p_ready[s], 4);   // one arrive per softmax warp of the stream
       mbar_init(&o_full[s], 1);
     }
     fence_mbar_init();
   }
-  if (warp == 5) {
+  if (warp == 9) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -148,108 +153,138 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   // key/value block range of a query tile: from the segment start of its first row to the segment end of its last
-  auto kv_range = [&](int tile, int& kv_lo, int& nblk) {
-    const int r0 = tile * TQ;
+  auto kv_range = [&](int item, int& kv_lo, int& nblk) {
+    if (item >= n_items) { kv_lo = 0; nblk = 0; return; }
+    const int r0 = (item / num_heads) * TQ;
     const int r1 = min(r0 + TQ, n_rows) - 1;
     kv_lo = seg[r0].x;
     nblk = (seg[r1].y - kv_lo + TK - 1) / TK;
   };
 
-  if (warp == 4) {
+  // Items of this CTA are taken in pairs (stream 0, stream 1).  Producer and MMA issuer walk one fixed order of
+  // (stream, block): (0,0) (1,0) then, after each P V of (x, j), (x, j+1) — so while one stream's softmax warps work
+  // on their scores the tensor core runs the other stream's S / P V, and K|V stages are consumed in the order they
+  // were loaded.
+  if (warp == 8) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      uint32_t it = 0, item_no = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_no) {
+      uint32_t it = 0, pair_no = 0;
+      auto load_q = [&](int x, int item) {
         const int tile = item / num_heads, head = item % num_heads;
-        int kv_lo, nblk;
-        kv_range(tile, kv_lo, nblk);
-        mbar_wait(q_empty, (item_no & 1u) ^ 1u);     // the previous item's S MMAs have read Q
-        mbar_expect_tx(q_full, TILE_BYTES);
-        tma_load_2d(smem + OFF_Q, &tm64, q_full, head * HD, tile * TQ);
-        tma_load_2d(smem + OFF_Q + Q64_BYTES, &tm16, q_full, head * HD + 64, tile * TQ);
-        for (int j = 0; j < nblk; ++j, ++it) {
-          const uint32_t s = it % KV_STAGES, ph = (it / KV_STAGES) & 1u;
-          mbar_wait(&kv_empty[s], ph ^ 1u);
-          uint8_t* kb = smem + OFF_KV + s * KV_STAGE_BYTES;
-          const int row = kv_lo + j * TK;
-          mbar_expect_tx(&kv_full[s], KV_STAGE_BYTES);
-          tma_load_2d(kb, &tm64, &kv_full[s], hidden + head * HD, row);
-          tma_load_2d(kb + Q64_BYTES, &tm16, &kv_full[s], hidden + head * HD + 64, row);
-          tma_load_2d(kb + TILE_BYTES, &tm64, &kv_full[s], 2 * hidden + head * HD, row);
-          tma_load_2d(kb + TILE_BYTES + Q64_BYTES, &tm16, &kv_full[s], 2 * hidden + head * HD + 64, row);
-        }
+        mbar_wait(&q_empty[x], (pair_no & 1u) ^ 1u);     // the stream's previous item's S MMAs have read Q
+        uint8_t* q = smem + OFF_Q + x * TILE_BYTES;
+        mbar_expect_tx(&q_full[x], TILE_BYTES);
+        tma_load_2d(q, &tm64, &q_full[x], head * HD, tile * TQ);
+        tma_load_2d(q + Q64_BYTES, &tm16, &q_full[x], head * HD + 64, tile * TQ);
+      };
+      auto load_kv = [&](int item, int kv_lo, int j) {
+        const int head = item % num_heads;
+        const uint32_t s = it % KV_STAGES, ph = (it / KV_STAGES) & 1u;
+        ++it;
+        mbar_wait(&kv_empty[s], ph ^ 1u);
+        uint8_t* kb = smem + OFF_KV + s * KV_STAGE_BYTES;
+        const int row = kv_lo + j * TK;
+        mbar_expect_tx(&kv_full[s], KV_STAGE_BYTES);
+        tma_load_2d(kb, &tm64, &kv_full[s], hidden + head * HD, row);
+        tma_load_2d(kb + Q64_BYTES, &tm16, &kv_full[s], hidden + head * HD + 64, row);
+        tma_load_2d(kb + TILE_BYTES, &tm64, &kv_full[s], 2 * hidden + head * HD, row);
+        tma_load_2d(kb + TILE_BYTES + Q64_BYTES, &tm16, &kv_full[s], 2 * hidden + head * HD + 64, row);
+      };
+      for (int item0 = blockIdx.x; item0 < n_items; item0 += 2 * gridDim.x, ++pair_no) {
+        const int item1 = item0 + gridDim.x;
+        int lo[2], nb[2];
+        kv_range(item0, lo[0], nb[0]);
+        kv_range(item1, lo[1], nb[1]);
+        const int items[2] = {item0, item1};
+        for (int x = 0; x < 2; ++x)
+          if (nb[x] > 0) {
+            load_q(x, items[x]);
+            load_kv(items[x], lo[x], 0);
+          }
+        const int nmax = max(nb[0], nb[1]);
+        for (int j = 0; j < nmax; ++j)
+          for (int x = 0; x < 2; ++x)
+            if (j + 1 < nb[x]) load_kv(items[x], lo[x], j + 1);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       constexpr uint32_t id_s = idesc_bf16(TQ, TK, false);
       constexpr uint32_t id_o64 = idesc_bf16(TQ, 64, true);
       constexpr uint32_t id_o16 = idesc_bf16(TQ, 16, true);
-      const uint32_t q_addr = smem_u32(smem + OFF_Q);
-      uint32_t it = 0;      // kv ring position of the NEXT block whose S has not been issued
-      uint32_t blk = 0;     // global block counter: S / P / O buffer = blk & 1
-      uint32_t item_no = 0;
-      auto issue_s = [&](uint32_t stage, uint32_t b) {   // S_b = Q K^T
-        const uint32_t k_addr = smem_u32(smem + OFF_KV + stage * KV_STAGE_BYTES);
-        const uint32_t d = tmem_base + TM_S + (b & 1u) * TK;
+      uint32_t it = 0;              // K|V ring position of the next block whose S has not been issued
+      uint32_t nblk_done[2] = {0, 0};  // blocks of each stream whose S / P V have been issued (barrier phases)
+      uint32_t npv_done[2] = {0, 0};
+      uint32_t stage_of[2] = {0, 0};   // ring stage holding the stream's current block
+      uint32_t pair_no = 0;
+      auto issue_s = [&](int x, bool last) {   // S_x = Q_x K^T for the stream's next block
+        const uint32_t s = it % KV_STAGES, ph = (it / KV_STAGES) & 1u;
+        ++it;
+        mbar_wait(&kv_full[s], ph);
+        tc_fence_after();
+        stage_of[x] = s;
+        const uint32_t q_addr = smem_u32(smem + OFF_Q + x * TILE_BYTES);
+        const uint32_t k_addr = smem_u32(smem + OFF_KV + s * KV_STAGE_BYTES);
+        const uint32_t d = tmem_base + TM_S + x * TK;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16(d, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), id_s, k != 0 ? 1u : 0u);
         umma_bf16(d, desc_k_sw32(q_addr + Q64_BYTES), desc_k_sw32(k_addr + Q64_BYTES), id_s, 1u);
-        umma_commit(&s_full[b & 1u]);
+        umma_commit(&s_full[x]);
+        if (last) umma_commit(&q_empty[x]);   // every S MMA of the item has been issued: Q is free once they retire
+        ++nblk_done[x];
       };
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_no) {
-        const int tile = item / num_heads;
-        int kv_lo, nblk;
-        kv_range(tile, kv_lo, nblk);
-        mbar_wait(q_full, item_no & 1u);
-        // first S of the item
-        {
-          const uint32_t s = it % KV_STAGES, ph = (it / KV_STAGES) & 1u;
-          mbar_wait(&kv_full[s], ph);
-          tc_fence_after();
-          issue_s(s, blk);
-        }
-        for (int j = 0; j < nblk; ++j) {
-          const uint32_t s = (it + j) % KV_STAGES;
-          const uint32_t b = blk + j;
-          if (j + 1 < nblk) {   // S of the next block runs while the softmax warps work on this one
-            const uint32_t s1 = (it + j + 1) % KV_STAGES, ph1 = ((it + j + 1) / KV_STAGES) & 1u;
-            mbar_wait(&kv_full[s1], ph1);
-            tc_fence_after();
-            issue_s(s1, b + 1);
-          } else {
-            umma_commit(q_empty);   // every S MMA of this item has been issued: Q is free once they retire
-          }
-          mbar_wait(&p_ready[b & 1u], (b >> 1) & 1u);   // P_j is in shared memory (and O buffer b&1 has been consumed)
-          tc_fence_after();
-          const uint32_t p_addr = smem_u32(smem + OFF_P + (b & 1u) * P_BYTES);
-          const uint32_t v_addr = smem_u32(smem + OFF_KV + s * KV_STAGE_BYTES + TILE_BYTES);
-          const uint32_t d = tmem_base + TM_O + (b & 1u) * TM_O_STRIDE;
+      auto issue_pv = [&](int x) {            // O_x = P_x V for the stream's current block
+        mbar_wait(&p_ready[x], npv_done[x] & 1u);   // P is in shared memory, the previous O has been folded
+        tc_fence_after();
+        ++npv_done[x];
+        const uint32_t s = stage_of[x];
+        const uint32_t p_addr = smem_u32(smem + OFF_P + x * P_BYTES);
+        const uint32_t v_addr = smem_u32(smem + OFF_KV + s * KV_STAGE_BYTES + TILE_BYTES);
+        const uint32_t d = tmem_base + TM_O + x * TM_O_STRIDE;
 #pragma unroll
-          for (int kk = 0; kk < TK / 16; ++kk) {
-            const uint64_t da = umma_desc_sw128(p_addr + (kk >> 2) * (TQ * 128) + (kk & 3) * 32);
-            umma_bf16(d, da, desc_mn_sw128(v_addr + kk * 2048), id_o64, kk != 0 ? 1u : 0u);
-            umma_bf16(d + 64, da, desc_mn_sw32(v_addr + Q64_BYTES + kk * 512), id_o16, kk != 0 ? 1u : 0u);
-          }
-          umma_commit(&kv_empty[s]);        // K_j (read by S_j earlier) and V_j are free once these retire
-          umma_commit(&o_full[b & 1u]);
+        for (int kk = 0; kk < TK / 16; ++kk) {
+          const uint64_t da = umma_desc_sw128(p_addr + (kk >> 2) * (TQ * 128) + (kk & 3) * 32);
+          umma_bf16(d, da, desc_mn_sw128(v_addr + kk * 2048), id_o64, kk != 0 ? 1u : 0u);
+          umma_bf16(d + 64, da, desc_mn_sw32(v_addr + Q64_BYTES + kk * 512), id_o16, kk != 0 ? 1u : 0u);
         }
-        it += nblk;
-        blk += nblk;
+        umma_commit(&kv_empty[s]);        // K (read by S earlier) and V of this block are free once these retire
+        umma_commit(&o_full[x]);
+      };
+      for (int item0 = blockIdx.x; item0 < n_items; item0 += 2 * gridDim.x, ++pair_no) {
+        const int item1 = item0 + gridDim.x;
+        int lo[2], nb[2];
+        kv_range(item0, lo[0], nb[0]);
+        kv_range(item1, lo[1], nb[1]);
+        for (int x = 0; x < 2; ++x)
+          if (nb[x] > 0) {
+            mbar_wait(&q_full[x], pair_no & 1u);
+            issue_s(x, nb[x] == 1);
+          }
+        const int nmax = max(nb[0], nb[1]);
+        for (int j = 0; j < nmax; ++j)
+          for (int x = 0; x < 2; ++x)
+            if (j < nb[x]) {
+              issue_pv(x);
+              if (j + 1 < nb[x]) issue_s(x, j + 2 == nb[x]);
+            }
       }
     }
   } else {
-    // ------------------------------------------------------------ softmax warps: thread = query row = TMEM lane
-    const int tid = threadIdx.x;              // 0..127
-    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    uint32_t blk = 0;
-    uint32_t item_no = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++item_no) {
+    // ------------------------------------------------------------ softmax warpgroups: stream x = warp / 4,
+    //                                                              thread = query row = TMEM lane
+    const int x = warp >> 2;
+    const int tid = threadIdx.x & 127;
+    const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    const uint32_t ts = lane_addr + TM_S + x * TK;
+    const uint32_t to = lane_addr + TM_O + x * TM_O_STRIDE;
+    uint8_t* pbuf = smem + OFF_P + x * P_BYTES;
+    uint32_t nblk_done = 0;   // blocks of this stream processed so far (barrier phases)
+    for (int item = blockIdx.x + x * gridDim.x; item < n_items; item += 2 * gridDim.x) {
       const int tile = item / num_heads, head = item % num_heads;
       int kv_lo, nblk;
-      kv_range(tile, kv_lo, nblk);
+      kv_range(item, kv_lo, nblk);
       const int r = tile * TQ + tid;
       int lo = 0, hi = 0;
       if (r < n_rows) {
@@ -262,25 +297,27 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
       for (int i = 0; i < HD; ++i) o[i] = 0.f;
       float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
 
-      auto fold = [&](uint32_t b, float corr) {   // o = o * corr + O_b
-        mbar_wait(&o_full[b & 1u], (b >> 1) & 1u);
+      auto fold = [&](uint32_t b, float corr) {   // o = o * corr + O of block b (single O buffer per stream)
+        mbar_wait(&o_full[x], b & 1u);
         tc_fence_after();
-        const uint32_t ta = lane_addr + TM_O + (b & 1u) * TM_O_STRIDE;
         uint32_t v[HD];
-        tmem_ld32(ta, v);
-        tmem_ld32(ta + 32, v + 32);
-        tmem_ld16(ta + 64, v + 64);
+        tmem_ld32(to, v);
+        tmem_ld32(to + 32, v + 32);
+        tmem_ld16(to + 64, v + 64);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < HD; ++i) o[i] = fmaf(o[i], corr, __uint_as_float(v[i]));
         tc_fence_before();
       };
 
+      // the previous item's TMA store has read the staging area that aliases this stream's P buffer
+      if (tid == 0) tma_store_wait_read<0>();
+      named_bar_sync(1 + x, 128);
+
       for (int j = 0; j < nblk; ++j) {
-        const uint32_t b = blk + j;
+        const uint32_t b = nblk_done + j;
         const int c_lo = lo - (kv_lo + j * TK), c_hi = hi - (kv_lo + j * TK);   // this row's valid columns of the block
-        const uint32_t ts = lane_addr + TM_S + (b & 1u) * TK;
-        mbar_wait(&s_full[b & 1u], (b >> 1) & 1u);
+        mbar_wait(&s_full[x], b & 1u);
         tc_fence_after();
         // Each 64-column half of the block is, for this row, entirely inside its segment (no masking), entirely
         // outside (skipped: P = 0) or cut by a segment boundary (masked element by element).
@@ -321,29 +358,29 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
         const float corr = m_run == -INFINITY ? 0.f : ex2_approx(m_run * scale_log2 - m_scaled);
         m_run = m_new;
         // pass 2: probabilities -> bf16 -> shared memory in the K-major SWIZZLE_128B layout the P V MMAs read
-        uint8_t* prow = smem + OFF_P + (b & 1u) * P_BYTES + tid * 128;
+        uint8_t* prow = pbuf + tid * 128;
         float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll 1
-        for (int c0 = 0; c0 < TK; c0 += 64) {
+        for (int c0 = 0; c0 < TK; c0 += 32) {
           uint8_t* atom = prow + (c0 >> 6) * (TQ * 128);     // 64 key columns = one swizzle atom row of 128 bytes
-          const bool outside = c_hi <= c0 || c_lo >= c0 + 64;
+          const int ch0 = (c0 & 63) >> 3;
+          const bool outside = c_hi <= c0 || c_lo >= c0 + 32;
           if (__all_sync(0xffffffffu, outside)) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) *reinterpret_cast<uint4*>(atom + ((q ^ (tid & 7)) << 4)) = make_uint4(0, 0, 0, 0);
+            for (int q = 0; q < 4; ++q) *reinterpret_cast<uint4*>(atom + (((ch0 + q) ^ (tid & 7)) << 4)) = make_uint4(0, 0, 0, 0);
             continue;
           }
-          const bool interior = c_lo <= c0 && c_hi >= c0 + 64;
-          uint32_t v[64];
+          const bool interior = c_lo <= c0 && c_hi >= c0 + 32;
+          uint32_t v[32];
           tmem_ld32(ts + c0, v);
-          tmem_ld32(ts + c0 + 32, v + 32);
           tmem_ld_wait();
-          uint32_t pk[32];
+          uint32_t pk[16];
           if (outside) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) pk[i] = 0u;
+            for (int i = 0; i < 16; ++i) pk[i] = 0u;
           } else if (interior) {
 #pragma unroll
-            for (int i = 0; i < 64; i += 2) {
+            for (int i = 0; i < 32; i += 2) {
               const float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), scale_log2, -m_scaled));
               const float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), scale_log2, -m_scaled));
               rs0 += p0;
@@ -352,7 +389,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
             }
           } else {
 #pragma unroll
-            for (int i = 0; i < 64; i += 2) {
+            for (int i = 0; i < 32; i += 2) {
               const int c = c0 + i;
               const float p0 = (c >= c_lo && c < c_hi) ? ex2_approx(fmaf(__uint_as_float(v[i]), scale_log2, -m_scaled)) : 0.f;
               const float p1 = (c + 1 >= c_lo && c + 1 < c_hi) ? ex2_approx(fmaf(__uint_as_float(v[i + 1]), scale_log2, -m_scaled)) : 0.f;
@@ -362,28 +399,28 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
             }
           }
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<uint4*>(atom + ((q ^ (tid & 7)) << 4)) =
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(atom + (((ch0 + q) ^ (tid & 7)) << 4)) =
                 make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         }
-        const float rs = rs0 + rs1;
-        l_run = l_run * corr + rs;
-        tc_fence_before();       // this thread's TMEM reads of S_b are complete (tcgen05.wait::ld above)
-        fence_proxy_async();     // P_b visible to the tensor core's shared-memory reads
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_ready[b & 1u]);
-        // fold the previous block's output in while the tensor core works on this one
+        l_run = l_run * corr + (rs0 + rs1);
+        tc_fence_before();       // this thread's TMEM reads of S are complete (tcgen05.wait::ld above)
+        // fold the previous block's output BEFORE releasing P: the stream has one O buffer and the P V that
+        // p_ready allows overwrites it
         if (j > 0) fold(b - 1, corr_prev);
         corr_prev = corr;
+        fence_proxy_async();     // P visible to the tensor core's shared-memory reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[x]);
       }
-      fold(blk + nblk - 1, corr_prev);
-      blk += nblk;
+      fold(nblk_done + nblk - 1, corr_prev);
+      nblk_done += nblk;
 
-      // ---- normalise, stage [128 x 80] bf16 (two 40-column boxes, 80-byte rows: conflict-free), one TMA store
+      // ---- normalise, stage [128 x 80] bf16 (two 40-column boxes, 80-byte rows: conflict-free) in the P buffer
+      //      (its last P V has retired: o_full was just waited on), one TMA store
       const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
-      if (tid == 0) tma_store_wait_read<0>();    // the previous item's store has read the staging buffer
-      named_bar_sync(1, 128);
-      uint8_t* orow = smem + OFF_OUT + tid * 80;
+      named_bar_sync(1 + x, 128);              // every row of the stream has finished reading O / is past its P writes
+      uint8_t* orow = pbuf + tid * 80;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
 #pragma unroll
@@ -395,10 +432,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
         }
       }
       fence_proxy_async();
-      named_bar_sync(1, 128);
+      named_bar_sync(1 + x, 128);
       if (tid == 0) {
-        tma_store_2d(&tmOut, smem + OFF_OUT, head * HD, tile * TQ);
-        tma_store_2d(&tmOut, smem + OFF_OUT + TQ * 80, head * HD + 40, tile * TQ);
+        tma_store_2d(&tmOut, pbuf, head * HD, tile * TQ);
+        tma_store_2d(&tmOut, pbuf + TQ * 80, head * HD + 40, tile * TQ);
         tma_store_commit();
       }
     }
@@ -407,7 +444,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc(tmem_base, 512);
+  if (warp == 9) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace
@@ -430,7 +467,7 @@ cudaError_t attention_tc_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, co
   const int items = ((n_rows + TQ - 1) / TQ) * num_heads;
   const int grid = items < num_sms ? items : num_sms;
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
-  attn_tc_kernel<<<grid, 192, SMEM_BYTES, stream>>>(tm64, tm16, tmOut, seg, n_rows, num_heads, hidden, scale_log2);
+  attn_tc_kernel<<<grid, kThreads, SMEM_BYTES, stream>>>(tm64, tm16, tmOut, seg, n_rows, num_heads, hidden, scale_log2);
   return cudaGetLastError();
 }
 
