@@ -16,8 +16,11 @@ def main(path):
         if row.get("Metric Name") != "gpu__time_duration.sum":
             continue
         name = row["Kernel Name"]
-        m = re.search(r"gemm_kernel<(\d+), *(\d+)>", name)
-        if m:
+        m = re.search(r"gemm_kernel<\(?(?:int\))?(\d+), *\(?(?:int\))?(\d+)", name)
+        m2 = re.search(r"gemm2_kernel<\(?(?:int\))?(\d+)", name)
+        if m2:
+            key = f"gemm2_kernel<{EPI.get(m2.group(1), m2.group(1))}> (CTA pair)"
+        elif m:
             key = f"gemm_kernel<BN={m.group(1)}, {EPI.get(m.group(2), m.group(2))}>"
         else:
             key = re.sub(r"\(.*", "", name.split("::")[-1])
