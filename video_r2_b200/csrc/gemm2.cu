@@ -233,12 +233,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       auto load_x = [&](int st) {   // fp32 residual piece of sub-step st -> its buffer
         int m0, n0, n_blk;
         coords(st, m0, n0, n_blk);
-#ifdef RESID_EXPERIMENT
-        mbar_arrive(&aux_full[st % NB]);
-#else
         mbar_expect_tx(&aux_full[st % NB], kSubX);
         tma_load_2d(out_base + (st % NB) * kSubBytes, &tm0, &aux_full[st % NB], n0, m0);
-#endif
       };
       if (lane == 0)
         for (int st = 0; st < NB && st < n_sub; ++st) load_x(st);
@@ -249,11 +245,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mbar_wait(&store_ready[b], (st / NB) & 1u);
         if (lane == 0) {
           const uint8_t* xb = out_base + b * kSubBytes;
-#ifndef RESID_EXPERIMENT
           tma_store_2d(&tm0, xb, n0, m0);
           tma_store_2d(&tm1, xb + kSubX, n0, m0);
           tma_store_commit();
-#endif
         }
         if ((st & 7) == 7) {
           // sum of squares of the new residual rows over this tile's 256 columns: one value per (row, column block),
