@@ -214,7 +214,19 @@ def run_vr2(args, rank, local_rank, world):
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout at communicator creation: keep stdout to the one JSON line
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)          # creates the communicator now, inside the redirect
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     cfg = vr2.VisionConfig()
     tower = vr2.VisionTower(cfg, synth_state_dict(cfg, dev), device=dev, precision=args.precision)
 
