@@ -1,6 +1,10 @@
-// Persistent, warp-specialised tcgen05 GEMM for sm_100a.
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a — the single-CTA kernel.
 //
 //   C[M,N] = A[M,K] * W[N,K]^T      A, W: bf16, K-major      accumulate: fp32 in TMEM
+//
+// It runs the GEMMs the CTA-pair kernel (gemm2.cu) does not take: the patch embed (rows scatter through the window
+// permute), the merger (EPI_STORE: GELU, inverse permute / caller's scatter fused into the store) and every GEMM of
+// the split precision (SPLIT).  gemm_launch() routes the bf16-precision QKV / residual / gate|up GEMMs to gemm2.
 //
 // One CTA per SM loops over 128 x BN output tiles (tile id -> n fastest, so the
 // 148 resident CTAs share a band of A rows and all of W through L2).  Roles:
@@ -72,28 +76,6 @@ struct Stage {
   __device__ __forceinline__ uint4* h8(int row, int half) const {
     return reinterpret_cast<uint4*>(base + row * 32 + (half << 4));
   }
-  // global [32 x 16 fp32] piece (row pitch ld elements) -> staging; lanes cover 8 rows x 64 B per pass
-  __device__ __forceinline__ void load_f32(const float* g, int64_t ld, int rows_valid, int lane) const {
-    const int chunk = lane & 3;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int row = (lane >> 2) + 8 * k;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row < rows_valid) v = *reinterpret_cast<const float4*>(g + row * ld + chunk * 4);
-      *f4(row, chunk) = v;
-    }
-  }
-  // same, for a piece only `width` (8 or 16) columns wide
-  __device__ __forceinline__ void load_f32_w(const float* g, int64_t ld, int rows_valid, int lane, int width) const {
-    const int chunk = lane & 3;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int row = (lane >> 2) + 8 * k;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row < rows_valid && chunk * 4 < width) v = __ldg(reinterpret_cast<const float4*>(g + row * ld + chunk * 4));
-      *f4(row, chunk) = v;
-    }
-  }
   // The same [32 x width] fp32 piece, split so the global loads can be issued one chunk ahead of their use:
   // fetch() -> registers (coalesced: 8 rows x 64 B per instruction), put() -> staging.
   static __device__ __forceinline__ void fetch_f32(float4 (&pre)[4], const float* g, int64_t ld, int rows_valid, int lane,
@@ -125,15 +107,6 @@ struct Stage {
     for (int k = 0; k < 4; ++k) {
       const int row = (lane >> 2) + 8 * k;
       if (row < rows_valid) *reinterpret_cast<float4*>(g + row * ld + chunk * 4) = *f4(row, chunk);
-    }
-  }
-  // staging bf16 [32 x 16] -> global; lanes cover 16 rows x 32 B per pass
-  __device__ __forceinline__ void store_bf16(__nv_bfloat16* g, int64_t ld, int rows_valid, int lane) const {
-    const int half = lane & 1;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int row = (lane >> 1) + 16 * k;
-      if (row < rows_valid) *reinterpret_cast<uint4*>(g + row * ld + half * 8) = *h8(row, half);
     }
   }
   __device__ __forceinline__ void store_bf16_w(__nv_bfloat16* g, int64_t ld, int rows_valid, int lane, int width) const {

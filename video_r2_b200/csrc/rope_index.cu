@@ -157,23 +157,19 @@ rope_fill_kernel(const int64_t* __restrict__ ids, int B, int S, const int64_t* _
     if (ed_img > len && ed_vid > len) break;  // malformed row (HF would raise): stop placing vision items
     int64_t t, h, w;
     float spg;
-    bool is_video;
     int ed;
     if (ed_img < ed_vid) {
       const int64_t* g = image_thw + 3 * static_cast<int64_t>(min(img_i, max(n_img_total - 1, 0)));
       t = g[0]; h = g[1]; w = g[2];
       spg = 0.f;
-      is_video = false;
       ++img_i; --remain_img; ed = ed_img;
     } else {
       const int vi = min(vid_i, max(n_vid_total - 1, 0));
       const int64_t* g = video_thw + 3 * static_cast<int64_t>(vi);
       t = g[0]; h = g[1]; w = g[2];
       spg = spg_arr != nullptr ? spg_arr[vi] : 1.0f;
-      is_video = true;
       ++vid_i; --remain_vid; ed = ed_vid;
     }
-    (void)is_video;
     const int gt = static_cast<int>(t);
     const int gh = static_cast<int>(h / cfg.spatial_merge_size), gw = static_cast<int>(w / cfg.spatial_merge_size);
     const int text_len = ed - st;
