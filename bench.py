@@ -320,12 +320,12 @@ def run_vr2(args, rank, local_rank, world):
                 next(res)        # the consumer runs one step behind: step i-1's host buffers are complete here
         pipe.drain()
 
-    def timed_pipe(steps):
+    def timed_pipe(fn, steps):
         barrier()
         t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        run_pipe(steps)          # drain() returns when the last step's D2H has landed in host memory
+        fn(steps)                # drain() returns when the last step's D2H has landed in host memory
         e1.record()
         torch.cuda.synchronize()
         wall = (time.perf_counter() - t0) * 1e3
@@ -336,9 +336,28 @@ def run_vr2(args, rank, local_rank, world):
             ms = t.item()
         return ms
 
+    # the same from resized uint8 FRAMES (what decord + the CPU resize produce): 1 byte per pixel value up, rescale +
+    # normalise + patchify on the GPU (vr2.patchify, bit-exact with the HF processor) -- reported as e2e.from_frames
+    frames_host = [torch.randint(0, 256, (2 * me.grid[0][0] if len(me.grid) == 1 else 2, 3, CLIP[1] * 14, CLIP[2] * 14),
+                                 dtype=torch.uint8, generator=torch.Generator().manual_seed(7 + k)).pin_memory()
+                   for k in range(2)] if len(me.grid) == 1 else None
+
+    def run_pipe_frames(steps):
+        res = pipe.results()
+        for i in range(steps):
+            pipe.submit_frames(frames_host[i % 2], out_host=out_hosts[i % 2], input_ids_host=ids_host,
+                               video_grid_thw=vid_thw, second_per_grid_ts=spg, pos_host=pos_hosts[i % 2])
+            if i >= 1:
+                next(res)
+        pipe.drain()
+
     run_pipe(3)
-    ms_e2e = timed_pipe(args.steps) / args.steps
+    ms_e2e = timed_pipe(run_pipe, args.steps) / args.steps
     e2e_value = tokens_total / (ms_e2e * 1e-3)
+    ms_e2e_frames = None
+    if frames_host is not None and world == 1:
+        run_pipe_frames(3)
+        ms_e2e_frames = timed_pipe(run_pipe_frames, args.steps) / args.steps
     for i in range(2):
         step_e2e(i)
     ms_e2e_sync = timed(step_e2e, args.steps) / args.steps
@@ -433,7 +452,11 @@ def run_vr2(args, rank, local_rank, world):
                      "avg_launch_ms": gu_avg, "peak_source": peak_src + ", sustained bf16"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e, "api": "video_r2_b200.HostPipeline (pinned host in/out, copies overlapped)",
-                "sync_value": tokens_total / (ms_e2e_sync * 1e-3), "sync_ms_per_step": ms_e2e_sync},
+                "sync_value": tokens_total / (ms_e2e_sync * 1e-3), "sync_ms_per_step": ms_e2e_sync,
+                "from_frames": None if ms_e2e_frames is None else {
+                    "value": tokens_total / (ms_e2e_frames * 1e-3), "ms_per_step": ms_e2e_frames,
+                    "h2d_bytes_per_step": int(frames_host[0].numel()) + ids_host.numel() * 8,
+                    "what": "uint8 frames [32,3,448,448] up, rescale+normalise+patchify on the GPU, then the same path"}},
         "gpu_launches": launches * args.steps,
         "clocks": clocks,
         "breakdown_ms_per_step": {k: round(v[0] / 3, 4) for k, v in breakdown.items()},

@@ -226,6 +226,17 @@ int vr2_scatter_rows(const void* src_dev, int32_t src_dtype, void* dst_dev, int3
                      const int32_t* dest_rows_dev, int64_t n_rows, int64_t row_elems, int64_t ld_dst, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Frames -> tower input rows (after the resize): rescale + normalise + patchify of
+ * transformers Qwen2VLVideoProcessor._preprocess and the caller's cast to the tower dtype.
+ * frames_dev: [T, C, H, W] uint8 or fp32 (H, W multiples of patch*merge); mean_host / std_host: [C] fp32 ALREADY
+ * fused with the rescale factor as HF does (mean / rescale_factor, std / rescale_factor in fp32);
+ * out_dev: [ceil(T/Tp) * (H/P) * (W/P), C*Tp*P*P] fp32 or bf16, rows in the processor's order.  T not a multiple of
+ * temporal_patch_size repeats the last frame.  Bit-exact with the processor (fp32) and with its output cast to bf16. */
+int vr2_patchify(const void* frames_dev, int32_t frames_dtype, int32_t T, int32_t C, int32_t H, int32_t W,
+                 int32_t patch_size, int32_t temporal_patch_size, int32_t merge_size, const float* mean_host,
+                 const float* std_host, void* out_dev, int32_t out_dtype, void* stream);
+
+/* ------------------------------------------------------------------------
  * Single operators, exported so tests can pin each kernel against the oracle.
  * ---------------------------------------------------------------------- */
 /* C[M,N] = A[M,K] W[N,K]^T (+bias) (GELU optional); A, W bf16; out bf16 or fp32. */

@@ -95,5 +95,22 @@ def main():
         print("tower", name, out.shape, float(out.abs().max()))
 
 
+PATCHIFY_CASES = {"even_4x56x84": ((4, 56, 84), 0), "odd_5x28x56": ((5, 28, 56), 1), "single_1x28x28": ((1, 28, 28), 2)}
+
+
+def patchify_goldens():
+    """uint8 frames -> pixel_values_videos through the HF video processor itself (resize off)."""
+    from transformers.models.qwen2_vl.video_processing_qwen2_vl import Qwen2VLVideoProcessor
+    proc = Qwen2VLVideoProcessor(do_resize=False)
+    for name, ((T, H, W), seed) in PATCHIFY_CASES.items():
+        v = torch.randint(0, 256, (T, 3, H, W), dtype=torch.uint8, generator=torch.Generator().manual_seed(seed))
+        out = proc(videos=[v], return_tensors="pt", do_resize=False, do_sample_frames=False)
+        np.savez_compressed(os.path.join(HERE, f"patchify_{name}.npz"), frames=v.numpy(),
+                            out=out["pixel_values_videos"].numpy(), grid=out["video_grid_thw"].numpy()[0],
+                            mean=np.asarray(proc.image_mean), std=np.asarray(proc.image_std), rescale=proc.rescale_factor)
+        print("patchify", name, tuple(out["pixel_values_videos"].shape))
+
+
 if __name__ == "__main__":
     main()
+    patchify_goldens()

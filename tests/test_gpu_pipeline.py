@@ -28,3 +28,20 @@ def test_host_pipeline_matches_synchronous_path():
         rpos, _ = vr2.get_rope_index(i.cuda(), None, torch.tensor(g[:1]).cuda(), torch.tensor([1.5]).cuda(), None)
         assert emb.dtype == torch.bfloat16 and torch.equal(emb, ref.cpu())
         assert torch.equal(pos, rpos.cpu())
+
+
+def test_host_pipeline_from_uint8_frames_matches_processor_then_tower():
+    import video_r2_b200 as vr2
+    from oracle import patchify as P
+    cfg_o = T.TowerConfig(depth=2, fullatt_block_indexes=(1,))
+    tower = vr2.VisionTower(vr2.VisionConfig(depth=2, fullatt_block_indexes=(1,)), T.make_weights(cfg_o, seed=2), device="cuda:0")
+    pipe = vr2.HostPipeline(tower, depth=2)
+    clips = [torch.randint(0, 256, (t, 3, h, w), dtype=torch.uint8, generator=torch.Generator().manual_seed(k)).pin_memory()
+             for k, (t, h, w) in enumerate([(4, 112, 168), (5, 56, 56), (4, 112, 168)])]
+    for c in clips:
+        pipe.submit_frames(c)
+    got = pipe.drain()
+    for (emb, _), c in zip(got, clips):
+        rows, grid = P.patchify(c.numpy(), vr2.preprocess.OPENAI_CLIP_MEAN, vr2.preprocess.OPENAI_CLIP_STD)
+        ref = tower(torch.from_numpy(rows).to(torch.bfloat16).cuda(), [grid])     # the reference's path: processor, cast, tower
+        assert torch.equal(emb, ref.cpu())

@@ -10,10 +10,11 @@ from ._lib import LIB_PATH, Vr2Error, lib
 from .rope_index import RopeConfig, get_rope_index
 from .embed import embed_visual_tokens, scatter_rows, token_positions
 from .pipeline import HostPipeline
+from .preprocess import patchify
 from .tower import Plan, VisionConfig, VisionTower, gather_rows
 
 __all__ = ["LIB_PATH", "Vr2Error", "lib", "RopeConfig", "get_rope_index", "Plan", "VisionConfig", "VisionTower",
-           "gather_rows", "HostPipeline", "embed_visual_tokens", "scatter_rows", "token_positions", "install", "uninstall", "refresh"]
+           "gather_rows", "HostPipeline", "patchify", "embed_visual_tokens", "scatter_rows", "token_positions", "install", "uninstall", "refresh"]
 
 
 def install(*args, **kwargs):

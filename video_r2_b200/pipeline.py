@@ -18,6 +18,7 @@ import collections
 
 import torch
 
+from .preprocess import patchify
 from .rope_index import get_rope_index
 
 
@@ -31,7 +32,8 @@ class HostPipeline:
         self.rope_config = rope_config
         self.s_in = torch.cuda.Stream(self.dev)
         self.s_out = torch.cuda.Stream(self.dev)
-        self._in = [None] * depth          # device pixel buffers
+        self._in = [None] * depth          # device pixel / frame buffers
+        self._pix = [None] * depth         # device patch rows produced by patchify (submit_frames)
         self._ids = [None] * depth
         self._out = [None] * depth         # device embedding buffers
         self._compute_done = [None] * depth
@@ -47,8 +49,18 @@ class HostPipeline:
         return b
 
     @torch.no_grad()
+    def submit_frames(self, frames_host: torch.Tensor, **kw):
+        """Like submit(), from resized uint8 (or fp32) frames [T, 3, H, W] in pinned host memory: the upload is 1 byte
+        per pixel value and rescale + normalise + patchify (the HF video processor's CPU work) run on the GPU
+        (`vr2.patchify`).  One clip per call; grid_thw is derived from the frame shape."""
+        T, _, H, W = frames_host.shape
+        grid = [[-(-T // self.tower.cfg.temporal_patch_size), H // self.tower.cfg.patch_size, W // self.tower.cfg.patch_size]]
+        return self.submit(frames_host, grid, _frames=True, **kw)
+
+    @torch.no_grad()
     def submit(self, x_host: torch.Tensor, grid_thw, out_host: torch.Tensor = None, input_ids_host: torch.Tensor = None,
-               video_grid_thw=None, second_per_grid_ts=None, pos_host: torch.Tensor = None, out_dtype=None):
+               video_grid_thw=None, second_per_grid_ts=None, pos_host: torch.Tensor = None, out_dtype=None,
+               _frames: bool = False):
         """Enqueue one batch.  `grid_thw` describes x_host's rows; when `input_ids_host` is given the M-RoPE position
         ids of that batch are computed too (`video_grid_thw` / `second_per_grid_ts`: device or host tensors)."""
         slot = self._n % self.depth
@@ -73,6 +85,12 @@ class HostPipeline:
         if self._d2h_done[slot] is not None:
             cur.wait_event(self._d2h_done[slot])
         out_dev = self._buf(self._out, slot, (plan.num_tokens, self.tower.cfg.out_hidden_size), odt)
+        if _frames:
+            cfg = self.tower.cfg
+            pix = self._buf(self._pix, slot, (plan.num_patches, cfg.patch_dim), torch.bfloat16)
+            patchify(x_dev, patch_size=cfg.patch_size, temporal_patch_size=cfg.temporal_patch_size,
+                     merge_size=cfg.spatial_merge_size, out=pix)
+            x_dev = pix
         self.tower.forward(x_dev, plan, out=out_dev)
         pos_dev = None
         if ids_dev is not None:
