@@ -36,6 +36,13 @@ TEXT_BEFORE, TEXT_AFTER = 32, 64
 FLOP_PER_TOKEN = 5.261e9     # BASELINE.md §3 (dense layers + attention, algorithmic)
 
 
+def workload_desc(world: int) -> str:
+    tokens = world * CLIP[0] * CLIP[1] * CLIP[2] // 4
+    return (f"Video-R2 eval setting x{world}: {world} clip(s) of 32 frames 448x448 (grid_thw [16,32,32] each, "
+            f"{tokens} visual tokens), Qwen2.5-VL-7B vision tower random init + get_rope_index; "
+            "slices sharded over ranks, one all-gather of embeddings")
+
+
 def _peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -177,8 +184,8 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "Video-R2 eval setting: 32-frame 448x448 clip, grid_thw [16,32,32], + get_rope_index",
-                   "sample": sample, "reference": "transformers Qwen2_5_VisionTransformerPretrainedModel on host CPU"},
+        "config": {"workload": workload_desc(max(1, args.gpus)), "sample": sample,
+                   "reference": "transformers Qwen2_5_VisionTransformerPretrainedModel (fp32, sdpa) on the host CPU, rank 0 only"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -435,9 +442,7 @@ def run_vr2(args, rank, local_rank, world):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {
-            "workload": f"Video-R2 eval setting x{world}: {world} clip(s) of 32 frames 448x448 (grid_thw [16,32,32] each, "
-                        f"{tokens_total} visual tokens), Qwen2.5-VL-7B vision tower random init + get_rope_index; "
-                        "slices sharded over ranks, one all-gather of embeddings",
+            "workload": workload_desc(world),
             "frames_per_sec": value / per_clip * 2 * CLIP[0],
             "l2": "pixel inputs rotate over 4 buffers (154 MB > 126 MB L2); 1.35 GB of weights and 0.44 GB of "
                   "activations stream through HBM every step",
