@@ -165,28 +165,29 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == kProducerWarp) {
-    // ------------------------------------------------------------ TMA producer (one lane, both CTAs)
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
-        const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
-        const int n0 = (tile % num_n) * BN + static_cast<int>(rank) * L::half_n;
-        for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
-          const uint32_t s = it % C::stages;
-          const uint32_t ph = (it / C::stages) & 1u;
-          mbar_wait(&empty_bar[s], ph ^ 1u);
-          uint8_t* sa = smem + s * L::stage_bytes;
-          uint8_t* sb = sa + L::a_bytes;
-          const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);   // the leader's barrier tracks the pair
+    // ------------------------------------------------------------ TMA producer (whole warp, one elected lane issues)
+    uint32_t it = 0;
+    for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
+      const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
+      const int n0 = (tile % num_n) * BN + static_cast<int>(rank) * L::half_n;
+      for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+        const uint32_t s = it % C::stages;
+        const uint32_t ph = (it / C::stages) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        uint8_t* sa = smem + s * L::stage_bytes;
+        uint8_t* sb = sa + L::a_bytes;
+        const uint32_t bar = mapa_u32(smem_u32(&full_bar[s]), 0);   // the leader's barrier tracks the pair
+        if (elect_one()) {
           if (leader) mbar_expect_tx(&full_bar[s], 2 * L::stage_bytes);
           tma_load_2d_2cta(sa, &tmA, bar, kb * BK, m0);
           tma_load_2d_2cta(sb, &tmB, bar, kb * BK, n0);
         }
+        __syncwarp();
       }
     }
   } else if (warp == kMmaWarp) {
-    // ------------------------------------------------------------ MMA issuer (one lane of the leader CTA)
-    if (leader && lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA; whole warp, one elected lane)
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
       uint32_t it = 0;
       uint32_t local = 0;
@@ -203,15 +204,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + s * L::stage_bytes);
           const uint32_t b_addr = a_addr + L::a_bytes;
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < BK / UK; ++k) {
-            const uint64_t da = umma_desc_sw128(a_addr + k * UK * 2);
-            const uint64_t db = umma_desc_sw128(b_addr + k * UK * 2);
-            umma_bf16_2cta(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / UK; ++k) {
+              const uint64_t da = umma_desc_sw128(a_addr + k * UK * 2);
+              const uint64_t db = umma_desc_sw128(b_addr + k * UK * 2);
+              umma_bf16_2cta(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit_2cta(&empty_bar[s], 0x3);   // frees this stage in both CTAs
+            if (kb == num_k_blocks - 1) umma_commit_2cta(&acc_full[as], 0x3);   // accumulators of both CTAs complete
           }
-          umma_commit_2cta(&empty_bar[s], 0x3);   // frees this stage in both CTAs
+          __syncwarp();
         }
-        umma_commit_2cta(&acc_full[as], 0x3);     // accumulators of both CTAs complete
       }
     }
   } else if (warp == kStoreWarp) {

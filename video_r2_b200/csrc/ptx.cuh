@@ -12,6 +12,22 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a converged warp.  Single-thread instructions (tcgen05.mma / commit, TMA) are issued as
+//   if (elect_one()) { ... }
+// inside code the WHOLE warp executes with warp-uniform values: operands then live in uniform registers.  Putting
+// the loop itself under `if (lane == 0)` makes every operand thread-private in the compiler's eyes and each MMA costs
+// an ELECT + 5 x R2UR.BROADCAST + BRA.U.ANY waterfall (~30 instructions): the issuing thread, not the tensor core,
+// becomes the limit (ncu r01f: the issue loop's samples are spread evenly over ~125 instructions per k-block).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
