@@ -11,10 +11,10 @@
 // Persistent CTAs, 10 warps, TWO items in flight per CTA (streams 0 and 1, each with its own Q tile, S and O
 // accumulators in TMEM, P buffer and softmax warpgroup): while one stream's softmax warps work on their scores the
 // tensor core runs the other stream's MMAs, and the loads / stores of one item hide behind the other's compute.
-//   warp 8 (one lane)  TMA producer: Q per item, K|V blocks of both streams into one 3-stage ring, in the fixed
+//   warp 8             TMA producer: Q per item, K|V blocks of both streams into one 3-stage ring, in the fixed
 //                      (stream, block) order the MMA issuer consumes them.  A 128 x 80 operand tile is two boxes:
 //                      64 columns (128-byte swizzle) + 16 columns (32-byte swizzle).
-//   warp 9 (one lane)  tcgen05.mma issuer:  S = Q K_j^T (5 MMAs of 128x128x16),  O_j = P_j V_j (8 k-steps x
+//   warp 9             tcgen05.mma issuer:  S = Q K_j^T (5 MMAs of 128x128x16),  O_j = P_j V_j (8 k-steps x
 //                      {N=64, N=16}, V as an MN-major operand, fresh accumulator per block)
 //   warps 4x..4x+3     softmax of stream x, thread = query row = TMEM lane: row max, exp2, P_j -> shared memory
 //                      (bf16, the K-major 128B-swizzled layout the MMA reads), running max / sum; the block outputs
@@ -166,16 +166,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
   // on their scores the tensor core runs the other stream's S / P V, and K|V stages are consumed in the order they
   // were loaded.
   if (warp == 8) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // ------------------------------------------------------------ TMA producer (whole warp; one elected lane issues)
+    {
+      const bool issuer = elect_one();
       uint32_t it = 0, pair_no = 0;
       auto load_q = [&](int x, int item) {
         const int tile = item / num_heads, head = item % num_heads;
         mbar_wait(&q_empty[x], (pair_no & 1u) ^ 1u);     // the stream's previous item's S MMAs have read Q
         uint8_t* q = smem + OFF_Q + x * TILE_BYTES;
-        mbar_expect_tx(&q_full[x], TILE_BYTES);
-        tma_load_2d(q, &tm64, &q_full[x], head * HD, tile * TQ);
-        tma_load_2d(q + Q64_BYTES, &tm16, &q_full[x], head * HD + 64, tile * TQ);
+        if (issuer) {
+          mbar_expect_tx(&q_full[x], TILE_BYTES);
+          tma_load_2d(q, &tm64, &q_full[x], head * HD, tile * TQ);
+          tma_load_2d(q + Q64_BYTES, &tm16, &q_full[x], head * HD + 64, tile * TQ);
+        }
+        __syncwarp();
       };
       auto load_kv = [&](int item, int kv_lo, int j) {
         const int head = item % num_heads;
@@ -184,11 +188,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
         mbar_wait(&kv_empty[s], ph ^ 1u);
         uint8_t* kb = smem + OFF_KV + s * KV_STAGE_BYTES;
         const int row = kv_lo + j * TK;
-        mbar_expect_tx(&kv_full[s], KV_STAGE_BYTES);
-        tma_load_2d(kb, &tm64, &kv_full[s], hidden + head * HD, row);
-        tma_load_2d(kb + Q64_BYTES, &tm16, &kv_full[s], hidden + head * HD + 64, row);
-        tma_load_2d(kb + TILE_BYTES, &tm64, &kv_full[s], 2 * hidden + head * HD, row);
-        tma_load_2d(kb + TILE_BYTES + Q64_BYTES, &tm16, &kv_full[s], 2 * hidden + head * HD + 64, row);
+        if (issuer) {
+          mbar_expect_tx(&kv_full[s], KV_STAGE_BYTES);
+          tma_load_2d(kb, &tm64, &kv_full[s], hidden + head * HD, row);
+          tma_load_2d(kb + Q64_BYTES, &tm16, &kv_full[s], hidden + head * HD + 64, row);
+          tma_load_2d(kb + TILE_BYTES, &tm64, &kv_full[s], 2 * hidden + head * HD, row);
+          tma_load_2d(kb + TILE_BYTES + Q64_BYTES, &tm16, &kv_full[s], 2 * hidden + head * HD + 64, row);
+        }
+        __syncwarp();
       };
       for (int item0 = blockIdx.x; item0 < n_items; item0 += 2 * gridDim.x, ++pair_no) {
         const int item1 = item0 + gridDim.x;
@@ -208,8 +215,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
       }
     }
   } else if (warp == 9) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------ MMA issuer (whole warp; one elected lane issues)
+    {
+      const bool issuer = elect_one();
       constexpr uint32_t id_s = idesc_bf16(TQ, TK, false);
       constexpr uint32_t id_o64 = idesc_bf16(TQ, 64, true);
       constexpr uint32_t id_o16 = idesc_bf16(TQ, 16, true);
@@ -227,12 +235,15 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
         const uint32_t q_addr = smem_u32(smem + OFF_Q + x * TILE_BYTES);
         const uint32_t k_addr = smem_u32(smem + OFF_KV + s * KV_STAGE_BYTES);
         const uint32_t d = tmem_base + TM_S + x * TK;
+        if (issuer) {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(d, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), id_s, k != 0 ? 1u : 0u);
-        umma_bf16(d, desc_k_sw32(q_addr + Q64_BYTES), desc_k_sw32(k_addr + Q64_BYTES), id_s, 1u);
-        umma_commit(&s_full[x]);
-        if (last) umma_commit(&q_empty[x]);   // every S MMA of the item has been issued: Q is free once they retire
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), id_s, k != 0 ? 1u : 0u);
+          umma_bf16(d, desc_k_sw32(q_addr + Q64_BYTES), desc_k_sw32(k_addr + Q64_BYTES), id_s, 1u);
+          umma_commit(&s_full[x]);
+          if (last) umma_commit(&q_empty[x]);   // every S MMA of the item has been issued: Q is free once they retire
+        }
+        __syncwarp();
         ++nblk_done[x];
       };
       auto issue_pv = [&](int x) {            // O_x = P_x V for the stream's current block
@@ -243,14 +254,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
         const uint32_t p_addr = smem_u32(smem + OFF_P + x * P_BYTES);
         const uint32_t v_addr = smem_u32(smem + OFF_KV + s * KV_STAGE_BYTES + TILE_BYTES);
         const uint32_t d = tmem_base + TM_O + x * TM_O_STRIDE;
+        if (issuer) {
 #pragma unroll
-        for (int kk = 0; kk < TK / 16; ++kk) {
-          const uint64_t da = umma_desc_sw128(p_addr + (kk >> 2) * (TQ * 128) + (kk & 3) * 32);
-          umma_bf16(d, da, desc_mn_sw128(v_addr + kk * 2048), id_o64, kk != 0 ? 1u : 0u);
-          umma_bf16(d + 64, da, desc_mn_sw32(v_addr + Q64_BYTES + kk * 512), id_o16, kk != 0 ? 1u : 0u);
+          for (int kk = 0; kk < TK / 16; ++kk) {
+            const uint64_t da = umma_desc_sw128(p_addr + (kk >> 2) * (TQ * 128) + (kk & 3) * 32);
+            umma_bf16(d, da, desc_mn_sw128(v_addr + kk * 2048), id_o64, kk != 0 ? 1u : 0u);
+            umma_bf16(d + 64, da, desc_mn_sw32(v_addr + Q64_BYTES + kk * 512), id_o16, kk != 0 ? 1u : 0u);
+          }
+          umma_commit(&kv_empty[s]);        // K (read by S earlier) and V of this block are free once these retire
+          umma_commit(&o_full[x]);
         }
-        umma_commit(&kv_empty[s]);        // K (read by S earlier) and V of this block are free once these retire
-        umma_commit(&o_full[x]);
+        __syncwarp();
       };
       for (int item0 = blockIdx.x; item0 < n_items; item0 += 2 * gridDim.x, ++pair_no) {
         const int item1 = item0 + gridDim.x;

@@ -215,44 +215,45 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == kProducerWarp) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / num_n_blocks) * BM;
-        const int n0 = (tile % num_n_blocks) * BN;
-        for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
-          const uint32_t s = it % C::stages;
-          const uint32_t ph = (it / C::stages) & 1u;
-          mbar_wait(&empty_bar[s], ph ^ 1u);
-          uint8_t* sa = smem + s * C::stage_bytes;
-          uint8_t* sb = sa + C::a_bytes;
+    // ------------------------------------------------------------ TMA producer (whole warp; one elected lane issues)
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / num_n_blocks) * BM;
+      const int n0 = (tile % num_n_blocks) * BN;
+      for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+        const uint32_t s = it % C::stages;
+        const uint32_t ph = (it / C::stages) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        uint8_t* sa = smem + s * C::stage_bytes;
+        uint8_t* sb = sa + C::a_bytes;
+        if (elect_one()) {
           mbar_expect_tx(&full_bar[s], C::stage_bytes);
           tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, m0);
           if constexpr (SPLIT) tma_load_2d(sa + C::a_half, &tmA2, &full_bar[s], kb * BK, m0);
           tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, n0);
         }
+        __syncwarp();
       }
     }
   } else if (warp == kMmaWarp) {
-    // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-      uint32_t it = 0;
-      uint32_t local = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
-        const uint32_t as = local & 1u;
-        const uint32_t use = local >> 1;
-        mbar_wait(&acc_empty[as], (use & 1u) ^ 1u);
+    // ------------------------------------------------------------ MMA issuer (whole warp; one elected lane issues)
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    uint32_t it = 0;
+    uint32_t local = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++local) {
+      const uint32_t as = local & 1u;
+      const uint32_t use = local >> 1;
+      mbar_wait(&acc_empty[as], (use & 1u) ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * kAccStride;
+      for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+        const uint32_t s = it % C::stages;
+        const uint32_t ph = (it / C::stages) & 1u;
+        mbar_wait(&full_bar[s], ph);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * kAccStride;
-        for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
-          const uint32_t s = it % C::stages;
-          const uint32_t ph = (it / C::stages) & 1u;
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * C::stage_bytes);
-          const uint32_t b_addr = a_addr + C::a_bytes;
+        const uint32_t a_addr = smem_u32(smem + s * C::stage_bytes);
+        const uint32_t b_addr = a_addr + C::a_bytes;
+        if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
             const uint64_t da = umma_desc_sw128(a_addr + k * UK * 2);
@@ -268,8 +269,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
           umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
+          if (kb == num_k_blocks - 1) umma_commit(&acc_full[as]);    // accumulator complete -> epilogue
         }
-        umma_commit(&acc_full[as]);    // accumulator complete -> epilogue
+        __syncwarp();
       }
     }
   } else {

@@ -219,7 +219,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
   } else if (warp == kStoreWarp) {
-    // ------------------------------------------------------------ store warp: everything the epilogue moves by TMA
+    // ------------------------------------------------------------ store warp: everything the epilogue moves by TMA.
+    // The whole warp runs the loops (warp-uniform operands stay in uniform registers); one fixed elected lane issues
+    // the bulk copies and owns their bulk groups.
+    const bool issuer = elect_one();
     uint32_t local = 0;
     if constexpr (EPI == EPI_RESID) {
       // Sub-step st = 8 * (tile ordinal) + k covers tile columns [32k, 32k + 32) and uses buffer k & 3.  Per buffer:
@@ -237,17 +240,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       auto load_x = [&](int st) {   // fp32 residual piece of sub-step st -> its buffer
         int m0, n0, n_blk;
         coords(st, m0, n0, n_blk);
-        mbar_expect_tx(&aux_full[st % NB], kSubX);
-        tma_load_2d(out_base + (st % NB) * kSubBytes, &tm0, &aux_full[st % NB], n0, m0);
+        if (issuer) {
+          mbar_expect_tx(&aux_full[st % NB], kSubX);
+          tma_load_2d(out_base + (st % NB) * kSubBytes, &tm0, &aux_full[st % NB], n0, m0);
+        }
       };
-      if (lane == 0)
-        for (int st = 0; st < NB && st < n_sub; ++st) load_x(st);
+      for (int st = 0; st < NB && st < n_sub; ++st) load_x(st);
       for (int st = 0; st < n_sub; ++st) {
         int m0, n0, n_blk;
         coords(st, m0, n0, n_blk);
         const int b = st % NB;
         mbar_wait(&store_ready[b], (st / NB) & 1u);
-        if (lane == 0) {
+        if (issuer) {
           const uint8_t* xb = out_base + b * kSubBytes;
           tma_store_2d(&tm0, xb, n0, m0);
           tma_store_2d(&tm1, xb + kSubX, n0, m0);
@@ -262,52 +266,57 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const float sum = (red[row] + red[128 + row]) + (red[256 + row] + red[384 + row]);
             if (m0 + row < p.M) p.ssq[static_cast<int64_t>(n_blk) * p.M + m0 + row] = sum;
           }
-          __syncwarp();
         }
-        if (lane == 0 && st >= 1) {
+        if (st >= 1) {
           // refill one sub-step behind: the previous sub-step's stores have had a whole epilogue step to drain
-          tma_store_wait_read<1>();
+          if (issuer) tma_store_wait_read<1>();
           if (st - 1 + NB < n_sub) load_x(st - 1 + NB);
         }
+        __syncwarp();
       }
     } else if constexpr (EPI == EPI_QKV) {
-      if (lane == 0) {
-        auto load_cs = [&](int tile) {   // cos / sin rows of this CTA's 128 patches: 2 + 2 boxes of 20 fp32 columns
-          const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
+      auto load_cs = [&](int tile) {   // cos / sin rows of this CTA's 128 patches: 2 + 2 boxes of 20 fp32 columns
+        const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
+        if (issuer) {
           mbar_expect_tx(&aux_full[0], 4 * kBox);
           tma_load_2d(aux_base, &tm1, &aux_full[0], 0, m0);
           tma_load_2d(aux_base + kBox, &tm1, &aux_full[0], 20, m0);
           tma_load_2d(aux_base + 2 * kBox, &tm2, &aux_full[0], 0, m0);
           tma_load_2d(aux_base + 3 * kBox, &tm2, &aux_full[0], 20, m0);
-        };
-        if (tile_begin < tile_end) load_cs(tile_begin);
-        for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++local) {
-          const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
-          const int n0 = (tile % num_n) * BN;
-          mbar_wait(&store_ready[0], local & 1u);
-          // every epilogue warp is done with the tables: fetch the next row block's if the rows change
-          if (tile + 1 < tile_end && (tile + 1) / num_n != tile / num_n) load_cs(tile + 1);
+        }
+      };
+      if (tile_begin < tile_end) load_cs(tile_begin);
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++local) {
+        const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
+        const int n0 = (tile % num_n) * BN;
+        mbar_wait(&store_ready[0], local & 1u);
+        // every epilogue warp is done with the tables: fetch the next row block's if the rows change
+        if (tile + 1 < tile_end && (tile + 1) / num_n != tile / num_n) load_cs(tile + 1);
+        if (issuer) {
+#pragma unroll
           for (int b = 0; b < 6; ++b) tma_store_2d(&tm0, out_base + b * kBox, n0 + b * 40, m0);
           tma_store_commit();
           tma_store_wait_read<0>();
           mbar_arrive(&out_free[0]);
         }
+        __syncwarp();
       }
     } else {  // EPI_SWIGLU
-      if (lane == 0) {
-        for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++local) {
-          const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
-          const int n_blk = tile % num_n;
-          mbar_wait(&store_ready[0], local & 1u);
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++local) {
+        const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
+        const int n_blk = tile % num_n;
+        mbar_wait(&store_ready[0], local & 1u);
+        if (issuer) {
           tma_store_2d(&tm0, out_base, n_blk * (BN / 2), m0);
           tma_store_2d(&tm0, out_base + 16384, n_blk * (BN / 2) + 64, m0);
           tma_store_commit();
           tma_store_wait_read<0>();              // the store has read the buffer
           mbar_arrive(&out_free[0]);
         }
+        __syncwarp();
       }
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores complete before exit
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // all stores complete before exit
   } else {
     // ------------------------------------------------------------ epilogue warps: thread = accumulator row
     const int quarter = warp & 3;   // TMEM lane quarter this warp may read
