@@ -680,8 +680,8 @@ cudaError_t gemm_launch(const GemmArgs& a, int num_sms, cudaStream_t stream, con
   if (gemm2_supports(a)) {
     switch (a.epilogue) {
       case EPI_QKV:
-        if (a.bias == nullptr || a.ssq_in == nullptr || a.cos_tab == nullptr || a.sin_tab == nullptr || a.out_bf16 == nullptr) {
-          *err = "gemm: EPI_QKV needs bias/ssq/cos/sin/out";
+        if (a.bias == nullptr || a.ssq_in == nullptr || a.out_bf16 == nullptr) {
+          *err = "gemm: EPI_QKV needs bias/ssq/out";
           return cudaErrorInvalidValue;
         }
         break;

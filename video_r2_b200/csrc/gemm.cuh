@@ -49,6 +49,11 @@ struct GemmArgs {
   float eps;
   const float* cos_tab;    // EPI_QKV: [M, 40] fp32
   const float* sin_tab;
+  // EPI_QKV, CTA-pair kernel: the same angles indexed by position (plan.cuh pos_win / pos_tab); optional — without
+  // them (or with more than 64 positions) the single-CTA kernel runs with the per-row tables
+  const int32_t* pos_win;  // [M] hpos | wpos << 16
+  const float* pos_tab;    // [n_pos, 40]
+  int n_pos;
 };
 
 // Enqueues the GEMM on `stream`.  Returns cudaSuccess or the launch error; shape

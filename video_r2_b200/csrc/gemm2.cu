@@ -35,6 +35,7 @@ constexpr int BK = 64;           // one 128-byte swizzle atom of bf16
 constexpr int UK = 16;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
+constexpr int kMaxPos = 64;      // positions (patch rows / columns of one frame) the QKV kernel's rotary table holds
 constexpr int kBox = 128 * 80;   // one [128 rows x 80 bytes] epilogue box (20 fp32 or 40 bf16 columns)
 
 // V: reserved variant index (0 everywhere today).
@@ -43,9 +44,9 @@ struct Cfg2;
 
 template <>
 struct Cfg2<EPI_QKV, 0> {
-  static constexpr int BN = 240, groups = 3, stages = 4;
+  static constexpr int BN = 240, groups = 3, stages = 5;
   static constexpr int out_bytes = 6 * kBox;   // 3 heads x (first | second rotary half) boxes of 40 bf16 columns
-  static constexpr int aux_bytes = 4 * kBox;   // cos: 2 boxes of 20 fp32 columns, sin: 2 boxes
+  static constexpr int aux_bytes = kMaxPos * 160;   // cos | sin of every (h or w) position: [64][40] fp32
 };
 template <>
 struct Cfg2<EPI_SWIGLU, 0> {
@@ -138,8 +139,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tm0);
-    if constexpr (EPI != EPI_SWIGLU) tma_prefetch_desc(&tm1);
-    if constexpr (EPI == EPI_QKV) tma_prefetch_desc(&tm2);
+    if constexpr (EPI == EPI_RESID) tma_prefetch_desc(&tm1);
     for (int s = 0; s < C::stages; ++s) {
       mbar_init(&full_bar[s], 1);    // leader's: its own expect_tx arrive; both CTAs' bytes complete on it
       mbar_init(&empty_bar[s], 1);   // multicast tcgen05.commit arrives once in each CTA
@@ -275,23 +275,20 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         __syncwarp();
       }
     } else if constexpr (EPI == EPI_QKV) {
-      auto load_cs = [&](int tile) {   // cos / sin rows of this CTA's 128 patches: 2 + 2 boxes of 20 fp32 columns
-        const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
-        if (issuer) {
-          mbar_expect_tx(&aux_full[0], 4 * kBox);
-          tma_load_2d(aux_base, &tm1, &aux_full[0], 0, m0);
-          tma_load_2d(aux_base + kBox, &tm1, &aux_full[0], 20, m0);
-          tma_load_2d(aux_base + 2 * kBox, &tm2, &aux_full[0], 0, m0);
-          tma_load_2d(aux_base + 3 * kBox, &tm2, &aux_full[0], 20, m0);
-        }
-      };
-      if (tile_begin < tile_end) load_cs(tile_begin);
+      // the per-position rotary table (cos | sin of p * f_k, 160 bytes per position) goes to shared memory once
+      if (issuer) {
+        const uint32_t bytes = static_cast<uint32_t>(p.n_pos) * 160u;
+        mbar_expect_tx(&aux_full[0], bytes);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :
+                     : "r"(smem_u32(aux_base)), "l"(reinterpret_cast<uint64_t>(p.pos_tab)), "r"(bytes),
+                       "r"(smem_u32(&aux_full[0]))
+                     : "memory");
+      }
       for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++local) {
         const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
         const int n0 = (tile % num_n) * BN;
         mbar_wait(&store_ready[0], local & 1u);
-        // every epilogue warp is done with the tables: fetch the next row block's if the rows change
-        if (tile + 1 < tile_end && (tile + 1) / num_n != tile / num_n) load_cs(tile + 1);
         if (issuer) {
 #pragma unroll
           for (int b = 0; b < 6; ++b) tma_store_2d(&tm0, out_base + b * kBox, n0 + b * 40, m0);
@@ -324,7 +321,6 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int row = quarter * 32 + lane;   // row within the CTA's 128
     const uint32_t acc_empty_leader = mapa_u32(smem_u32(&acc_empty[0]), 0);
     uint32_t local = 0;
-    uint32_t aux_loads = 0;         // QKV: table loads consumed so far
     for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++local) {
       const int n_blk = tile % num_n;
       const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
@@ -398,14 +394,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int q = 0; q < p.ssq_parts; ++q) s += p.ssq_in[static_cast<int64_t>(q) * p.M + r];
           rstd = rsqrtf(s * p.inv_dim + p.eps);
         }
-        if (local == 0 || tile / num_n != (tile - 1) / num_n) {   // a new row block: its tables were (re)loaded
-          mbar_wait(&aux_full[0], aux_loads & 1u);
-          ++aux_loads;
-        }
+        int hw = 0;
+        if (valid) hw = __ldg(p.pos_win + r);                       // this row's (h, w) position in its frame
+        const uint8_t* tab_h = aux_base + (hw & 0xffff) * 160;      // angles 0..19 follow h, 20..39 follow w
+        const uint8_t* tab_w = aux_base + (hw >> 16) * 160;
+        if (local == 0) mbar_wait(&aux_full[0], 0);                 // the table has landed
         if (local > 0) mbar_wait(&out_free[0], (local - 1) & 1u);   // the previous tile's stores have drained
         mbar_wait_relaxed(&acc_full[as], use & 1u);
         tc_fence_after();
-        const uint8_t* cs_row = aux_base + row * 80;
         uint8_t* out_row = out_base + (cg * 2) * kBox + row * 80;
 #pragma unroll 1
         for (int i0 = 0; i0 < 40; i0 += 8) {
@@ -416,10 +412,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (rot) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-              const int f4 = i0 / 4 + j;              // float4 index within the 40 angles: box f4 / 5, chunk f4 % 5
-              const int off = (f4 / 5) * kBox + (f4 % 5) * 16;
-              const float4 c4 = *reinterpret_cast<const float4*>(cs_row + off);
-              const float4 s4 = *reinterpret_cast<const float4*>(cs_row + 2 * kBox + off);
+              const int f4 = i0 / 4 + j;              // float4 index within the 40 angles: h part 0..4, w part 5..9
+              const uint8_t* t = (f4 < 5 ? tab_h : tab_w) + (f4 % 5) * 16;
+              const float4 c4 = *reinterpret_cast<const float4*>(t);
+              const float4 s4 = *reinterpret_cast<const float4*>(t + 80);
               cs[4 * j] = c4.x; cs[4 * j + 1] = c4.y; cs[4 * j + 2] = c4.z; cs[4 * j + 3] = c4.w;
               sn[4 * j] = s4.x; sn[4 * j + 1] = s4.y; sn[4 * j + 2] = s4.z; sn[4 * j + 3] = s4.w;
             }
@@ -527,9 +523,9 @@ cudaError_t launch2(const GemmArgs& a, int num_sms, cudaStream_t stream, const c
   bool ok = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.A, a.K, a.M, a.lda * 2, BK, BM, true) &&
             encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.W, a.K, a.N, a.ldw * 2, BK, L::half_n, true);
   if (EPI == EPI_QKV) {
-    ok = ok && encode(&tm0, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.out_bf16, a.N, a.M, a.ld_out * 2, 40, BM, false) &&
-         encode(&tm1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.cos_tab, 40, a.M, 160, 20, BM, false) &&
-         encode(&tm2, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.sin_tab, 40, a.M, 160, 20, BM, false);
+    ok = ok && encode(&tm0, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.out_bf16, a.N, a.M, a.ld_out * 2, 40, BM, false);
+    tm1 = tm0;
+    tm2 = tm0;
   } else if (EPI == EPI_RESID) {
     ok = ok && tma_encode_2d_swz(&tm0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a.x, a.N, a.M, a.ldx * 4, 32, BM, 128) &&
          tma_encode_2d_swz(&tm1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.out_bf16, a.N, a.M, a.ld_out * 2, 32, BM, 64);
@@ -579,7 +575,7 @@ cudaError_t launch2(const GemmArgs& a, int num_sms, cudaStream_t stream, const c
 bool gemm2_supports(const GemmArgs& a) {
   if (a.A_lo != nullptr || a.row_map != nullptr) return false;
   switch (a.epilogue) {
-    case EPI_QKV: return a.N % 240 == 0 && (a.N / 3) % 80 == 0;
+    case EPI_QKV: return a.N % 240 == 0 && (a.N / 3) % 80 == 0 && a.pos_win != nullptr && a.pos_tab != nullptr && a.n_pos > 0 && a.n_pos <= kMaxPos;
     case EPI_RESID: return (a.flags & GEMM_ADD_RESID) != 0 && a.N % 256 == 0 && a.bias != nullptr;
     case EPI_SWIGLU: return a.N % 256 == 0;
     default: return false;

@@ -10,6 +10,7 @@
 // O(1), so no sort, no host loop and no .tolist().
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
@@ -30,7 +31,8 @@ __global__ void plan_tables_kernel(const ClipDesc* __restrict__ clips, int n_cli
                                    const float* __restrict__ inv_freq, int half_dim, int64_t* __restrict__ window_index,
                                    int64_t* __restrict__ reverse_index, int32_t* __restrict__ row_map,
                                    int32_t* __restrict__ out_map, int32_t* __restrict__ pos_hw,
-                                   float* __restrict__ cos_tab, float* __restrict__ sin_tab) {
+                                   float* __restrict__ cos_tab, float* __restrict__ sin_tab,
+                                   int32_t* __restrict__ pos_win) {
   const int64_t r = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // window-order patch row
   if (r >= n_tokens * 4) return;
   const int64_t p = r >> 2;
@@ -67,6 +69,7 @@ __global__ void plan_tables_kernel(const ClipDesc* __restrict__ clips, int n_cli
   row_map[src_row] = static_cast<int32_t>(r);
   pos_hw[src_row * 2 + 0] = hpos;
   pos_hw[src_row * 2 + 1] = wpos;
+  pos_win[r] = hpos | (wpos << 16);
   const int quarter = half_dim / 2;
   for (int k = 0; k < quarter; ++k) {
     const float f = inv_freq[k];
@@ -77,6 +80,18 @@ __global__ void plan_tables_kernel(const ClipDesc* __restrict__ clips, int n_cli
     cos_tab[r * half_dim + quarter + k] = cosf(aw);
     sin_tab[r * half_dim + quarter + k] = sinf(aw);
   }
+}
+
+// The same angles per POSITION instead of per row: tab[p][k] = cos(p * f_k), tab[p][quarter + k] = sin(p * f_k) —
+// bit-identical to the per-row tables (same expression), 160 bytes per position; the CTA-pair QKV GEMM keeps it in
+// shared memory and looks rows up through pos_win.
+__global__ void pos_table_kernel(const float* __restrict__ inv_freq, int quarter, int n_pos, float* __restrict__ tab) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pos * quarter) return;
+  const int p = i / quarter, k = i - p * quarter;
+  const float a = static_cast<float>(p) * inv_freq[k];
+  tab[p * 2 * quarter + k] = cosf(a);
+  tab[p * 2 * quarter + quarter + k] = sinf(a);
 }
 
 // dst[i,:] = src[index[i],:], 16-byte vectors; one warp per row chunk keeps the
@@ -187,7 +202,10 @@ extern "C" int vr2_plan_create(const vr2_plan_config* cfg, const int64_t* grid, 
     for (int r = cu_window[i]; r < cu_window[i + 1]; ++r) seg_w[r] = make_int2(cu_window[i], cu_window[i + 1]);
   for (size_t i = 0; i + 1 < cu_seq.size(); ++i)
     for (int r = cu_seq[i]; r < cu_seq[i + 1]; ++r) seg_f[r] = make_int2(cu_seq[i], cu_seq[i + 1]);
-  const size_t total = rnd(N * 8) * 2 + rnd(T * 8) * 2 + rnd(N * 4) + rnd(T * 4) + rnd(N * 8) + rnd(N * HDIM * 4) * 2 +
+  int n_pos = 0;
+  for (int c = 0; c < n_items; ++c) n_pos = std::max<int>(n_pos, static_cast<int>(std::max(grid[3 * c + 1], grid[3 * c + 2])));
+  plan->n_pos = n_pos;
+  const size_t total = rnd(N * 4) + rnd(static_cast<size_t>(n_pos) * HDIM * 4) + rnd(N * 8) * 2 + rnd(T * 8) * 2 + rnd(N * 4) + rnd(T * 4) + rnd(N * 8) + rnd(N * HDIM * 4) * 2 +
                        rnd(cu_window.size() * 4) + rnd(cu_seq.size() * 4) + rnd(tiles_w.size() * 16) +
                        rnd(tiles_f.size() * 16) + rnd(clips.size() * sizeof(ClipDesc)) + rnd(inv_freq.size() * 4);
   e = cudaMalloc(&plan->blob, total);
@@ -207,6 +225,8 @@ extern "C" int vr2_plan_create(const vr2_plan_config* cfg, const int64_t* grid, 
   plan->cu_seqlens = carve<int32_t>(cur, cu_seq.size());
   plan->tiles_window = carve<int4>(cur, tiles_w.size());
   plan->tiles_full = carve<int4>(cur, tiles_f.size());
+  plan->pos_win = carve<int32_t>(cur, N);
+  plan->pos_tab = carve<float>(cur, static_cast<size_t>(n_pos) * HDIM);
   plan->seg_window = carve<int2>(cur, N);
   plan->seg_full = carve<int2>(cur, N);
   ClipDesc* d_clips = carve<ClipDesc>(cur, clips.size());
@@ -226,8 +246,13 @@ extern "C" int vr2_plan_create(const vr2_plan_config* cfg, const int64_t* grid, 
     const int64_t blocks = (static_cast<int64_t>(N) + threads - 1) / threads;
     plan_tables_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(
         d_clips, n_items, plan->n_tokens, ws, d_inv, plan->half_dim, plan->window_index, plan->reverse_index,
-        plan->row_map, plan->out_map, plan->pos_hw, plan->cos_tab, plan->sin_tab);
+        plan->row_map, plan->out_map, plan->pos_hw, plan->cos_tab, plan->sin_tab, plan->pos_win);
     e = cudaGetLastError();
+    if (e == cudaSuccess) {
+      const int quarter = plan->half_dim / 2;
+      pos_table_kernel<<<(n_pos * quarter + 255) / 256, 256, 0, stream>>>(d_inv, quarter, n_pos, plan->pos_tab);
+      e = cudaGetLastError();
+    }
   }
   // the host staging vectors die with this frame: make the copies land first
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);

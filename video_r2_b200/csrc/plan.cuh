@@ -26,6 +26,9 @@ struct vr2_plan {
   int32_t* pos_hw = nullptr;         // [patches,2] original order
   float* cos_tab = nullptr;          // [patches, half_dim] window order
   float* sin_tab = nullptr;
+  int32_t* pos_win = nullptr;        // [patches] window order: hpos | wpos << 16
+  float* pos_tab = nullptr;          // [n_pos, half_dim]: cos(p * f_k) for k < half_dim/2, then sin(p * f_k)
+  int n_pos = 0;                     // max(h, w) over the clips (patch units)
   int32_t* cu_window = nullptr;      // [windows+1]
   int32_t* cu_seqlens = nullptr;     // [slices+1]
   int4* tiles_window = nullptr;      // attention query tiles for window layers (mma.sync kernel, split precision)

@@ -414,6 +414,7 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
       a.out_bf16 = w.qkv; a.out_lo = w.qkv_lo; a.ld_out = 3 * h;
       a.ssq_in = w.ssq; a.ssq_parts = parts; a.inv_dim = 1.0f / h; a.eps = eps;
       a.cos_tab = plan->cos_tab; a.sin_tab = plan->sin_tab;
+      a.pos_win = plan->pos_win; a.pos_tab = plan->pos_tab; a.n_pos = plan->n_pos;
       if ((rc = G(a, VR2_K_QKV, "qkv")) != VR2_OK) return rc;
     }
     {
