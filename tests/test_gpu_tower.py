@@ -125,3 +125,19 @@ def test_shape_errors_raise_value_error():
         tower(torch.zeros(10, 1176, device="cuda"), [[1, 4, 4]])
     with pytest.raises(ValueError):
         tower(torch.zeros(16, 1000, device="cuda"), [[1, 4, 4]])
+
+
+def test_tall_frame_uses_per_row_rotary_tables():
+    """More than 64 patch rows (frames taller than 896 px): the CTA-pair QKV kernel's 64-position table does not
+    apply and the single-CTA kernel with per-row tables runs instead — same numbers."""
+    cfg = T.TowerConfig(depth=2, fullatt_block_indexes=(1,))
+    w = T.make_weights(cfg, seed=12)
+    tower = _tower(cfg, w)
+    for grid in ([[1, 66, 6]], [[2, 64, 8]], [[1, 4, 70], [1, 8, 8]]):
+        n = sum(t * h * ww for t, h, ww in grid)
+        x = torch.randn(n, 1176, generator=torch.Generator().manual_seed(13)).to(torch.bfloat16)
+        ref = T.tower_forward(w, cfg, x.float(), grid)
+        out = tower(x.cuda(), grid, out_dtype=torch.float32)
+        e, c, r = _stats(out, ref)
+        print(f"\n{grid}: max-abs {e:.4f} cos {c:.6f}")
+        assert e <= 3e-2 and c >= 0.9995, (grid, e, c)
