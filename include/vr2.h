@@ -237,6 +237,18 @@ int vr2_patchify(const void* frames_dev, int32_t frames_dtype, int32_t T, int32_
                  const float* std_host, void* out_dev, int32_t out_dtype, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Decoder-side M-RoPE application: the consumer of vr2_rope_index's position ids.
+ * Replaces Qwen2_5_VLRotaryEmbedding.forward + apply_multimodal_rotary_pos_emb (transformers
+ * modeling_qwen2_5_vl.py; Liger's liger_multimodal_rotary_pos_emb in train_sft.py:83-84) with one kernel that forms
+ * cos/sin from position_ids on the fly.  q_dev [B, Hq, S, D], k_dev [B, Hk, S, D] (contiguous, fp32 or bf16; the
+ * outputs may alias the inputs), position_ids_dev [3, B, S] int64, inv_freq_dev [D/2] fp32 (the module's buffer),
+ * mrope_section_host [3] (sums to D/2; [16, 24, 24] for Qwen2.5-VL-7B), attention_scaling (1.0 for default rope).
+ * bf16: every product and the sum are rounded to bf16 as in HF's bf16 forward. */
+int vr2_mrope_apply(const void* q_dev, const void* k_dev, void* q_out_dev, void* k_out_dev, int32_t dtype, int32_t B,
+                    int32_t S, int32_t Hq, int32_t Hk, int32_t D, const int64_t* position_ids_dev,
+                    const float* inv_freq_dev, const int32_t* mrope_section_host, float attention_scaling, void* stream);
+
+/* ------------------------------------------------------------------------
  * Single operators, exported so tests can pin each kernel against the oracle.
  * ---------------------------------------------------------------------- */
 /* C[M,N] = A[M,K] W[N,K]^T (+bias) (GELU optional); A, W bf16; out bf16 or fp32. */

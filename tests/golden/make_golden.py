@@ -111,6 +111,30 @@ def patchify_goldens():
         print("patchify", name, tuple(out["pixel_values_videos"].shape))
 
 
+def mrope_goldens():
+    """q, k, position ids -> rotated q, k through HF's own rotary code (fp32 and bf16)."""
+    from transformers.models.qwen2_5_vl import modeling_qwen2_5_vl as M
+    g = torch.Generator().manual_seed(5)
+    B, S, Hq, Hk, D = 2, 19, 3, 2, 128
+    pos = torch.randint(0, 5000, (3, B, S), generator=g)
+    pos[:, 1, :4] = 1                                   # padding positions as get_rope_index writes them
+    inv = 1.0 / (1000000.0 ** (torch.arange(0, D, 2, dtype=torch.int64).float() / D))
+    out = {"pos": pos.numpy(), "inv_freq": inv.numpy(), "section": np.asarray([16, 24, 24])}
+    for name, dt in (("f32", torch.float32), ("bf16", torch.bfloat16)):
+        q = torch.randn(B, Hq, S, D, generator=g).to(dt)
+        k = torch.randn(B, Hk, S, D, generator=g).to(dt)
+        inv_e = inv[None, None, :, None].float().expand(3, B, -1, 1)      # Qwen2_5_VLRotaryEmbedding.forward
+        freqs = (inv_e @ pos[:, :, None, :].float()).transpose(2, 3)
+        emb = torch.cat((freqs, freqs), dim=-1)
+        cos, sin = emb.cos().to(dt), emb.sin().to(dt)
+        rq, rk = M.apply_multimodal_rotary_pos_emb(q, k, cos, sin, [16, 24, 24])
+        for key, t in (("q", q), ("k", k), ("rq", rq), ("rk", rk)):
+            out[f"{key}_{name}"] = t.float().numpy()      # bf16 values are exactly representable in fp32
+    np.savez_compressed(os.path.join(HERE, "mrope_small.npz"), **out)
+    print("mrope", out["rq_bf16"].shape)
+
+
 if __name__ == "__main__":
     main()
     patchify_goldens()
+    mrope_goldens()

@@ -86,6 +86,8 @@ SIGNATURES = {
     "vr2_scatter_rows": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P, C.c_int64, C.c_int64, C.c_int64, _P]),
     "vr2_patchify": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                C.POINTER(C.c_float), C.POINTER(C.c_float), _P, C.c_int32, _P]),
+    "vr2_mrope_apply": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P,
+                                  C.POINTER(C.c_int32), C.c_float, _P]),
     "vr2_tower_profile": (C.c_int, [_P, C.c_uint32]),
     "vr2_tower_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "vr2_tower_launch_count": (C.c_int64, [_P, _P, C.c_int32]),
