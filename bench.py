@@ -423,6 +423,31 @@ def run_vr2(args, rank, local_rank, world):
         same = torch.equal(ref_way(0), fused_way(0).clone())
         widening = {"what": "tower + placement of the visual tokens in inputs_embeds [1, %d, %d] bf16" % (len(row), cfg.out_hidden_size),
                     "forward_then_masked_scatter_ms": ms_ref, "fused_scatter_ms": ms_fused, "bit_identical": bool(same)}
+        # LM-head per-token log-probs without the logits tensor, vs matmul + log_softmax + gather
+        try:
+            Mt, Kt, Vt = 4096, 3584, 152064
+            gl = torch.Generator(device=dev).manual_seed(9)
+            hl = torch.randn(Mt, Kt, generator=gl, device=dev).to(torch.bfloat16)
+            wl = (torch.randn(Vt, Kt, generator=gl, device=dev) * 0.05).to(torch.bfloat16)
+            tl = torch.randint(0, Vt, (Mt,), generator=gl, device=dev)
+
+            def lp_fused(i):
+                return vr2.lm_logprob(hl, wl, tl, 1.0)
+
+            def lp_torch(i):
+                logits = hl @ wl.T
+                return torch.log_softmax(logits.float(), -1).gather(-1, tl[:, None]).squeeze(-1)
+
+            for fn in (lp_fused, lp_torch):
+                fn(0)
+            ms_lf = timed(lp_fused, 5) / 5
+            ms_lt = timed(lp_torch, 5) / 5
+            diff = (lp_fused(0) - lp_torch(0)).abs().max().item()
+            widening["lm_logprob"] = {"tokens": Mt, "vocab": Vt, "fused_ms": ms_lf, "matmul_log_softmax_ms": ms_lt,
+                                      "fused_tflops": 2.0 * Mt * Kt * Vt / (ms_lf * 1e-3) / 1e12, "max_abs_diff": diff}
+            del hl, wl, tl
+        except Exception as e:  # never let the optional measurement break the contract line
+            widening["lm_logprob"] = {"error": repr(e)}
 
     peaks, peak_src = _peaks()
     gu_ms, gu_n = prof.get("gate_up", (0.0, 0))

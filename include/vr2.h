@@ -249,6 +249,18 @@ int vr2_mrope_apply(const void* q_dev, const void* k_dev, void* q_out_dev, void*
                     const float* inv_freq_dev, const int32_t* mrope_section_host, float attention_scaling, void* stream);
 
 /* ------------------------------------------------------------------------
+ * LM-head per-token log-probabilities without materialising the logits.
+ * out[m] = log_softmax(hidden[m] @ W^T / temperature)[target[m]], fp32.  Replaces, in Video-R2's GRPO
+ * (train/src/trainer/grpo_trainer.py:723-741), lm_head -> logits / temperature -> selective_log_softmax, which writes
+ * and re-reads a [tokens, vocab] bf16 tensor.  hidden_dev [M, K] bf16, weight_dev [V, K] bf16 (lm_head.weight), target_dev
+ * [M] int64 (a target outside [0, V) yields NaN), workspace_dev: vr2_lm_logprob_workspace_bytes(M, V), 16-byte aligned.
+ * The contraction runs on the CTA-pair tcgen05 GEMM with fp32 accumulation; scores are not rounded to bf16. */
+size_t vr2_lm_logprob_workspace_bytes(int64_t M, int32_t V);
+int vr2_lm_logprob(const void* hidden_dev, const void* weight_dev, const int64_t* target_dev, int64_t M, int32_t V,
+                   int32_t K, float temperature, float* out_logprob_dev, void* workspace_dev, size_t workspace_bytes,
+                   void* stream);
+
+/* ------------------------------------------------------------------------
  * Single operators, exported so tests can pin each kernel against the oracle.
  * ---------------------------------------------------------------------- */
 /* C[M,N] = A[M,K] W[N,K]^T (+bias) (GELU optional); A, W bf16; out bf16 or fp32. */

@@ -9,13 +9,14 @@ Everything heavy lives in libvr2.so (video_r2_b200/csrc, C ABI in include/vr2.h)
 from ._lib import LIB_PATH, Vr2Error, lib
 from .rope_index import RopeConfig, get_rope_index
 from .embed import embed_visual_tokens, scatter_rows, token_positions
+from .logprob import lm_logprob
 from .mrope import apply_mrope
 from .pipeline import HostPipeline
 from .preprocess import patchify
 from .tower import Plan, VisionConfig, VisionTower, gather_rows
 
 __all__ = ["LIB_PATH", "Vr2Error", "lib", "RopeConfig", "get_rope_index", "Plan", "VisionConfig", "VisionTower",
-           "gather_rows", "HostPipeline", "patchify", "apply_mrope", "embed_visual_tokens", "scatter_rows", "token_positions", "install", "uninstall", "refresh"]
+           "gather_rows", "HostPipeline", "patchify", "apply_mrope", "lm_logprob", "embed_visual_tokens", "scatter_rows", "token_positions", "install", "uninstall", "refresh"]
 
 
 def install(*args, **kwargs):

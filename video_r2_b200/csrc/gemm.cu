@@ -691,6 +691,8 @@ cudaError_t gemm_launch(const GemmArgs& a, int num_sms, cudaStream_t stream, con
           return cudaErrorInvalidValue;
         }
         break;
+      case EPI_LOGPROB:
+        break;
       default:
         if (a.bias == nullptr || a.ssq_in == nullptr || a.out_bf16 == nullptr) {
           *err = "gemm: EPI_SWIGLU needs bias/ssq/out";
@@ -741,6 +743,9 @@ cudaError_t gemm_launch(const GemmArgs& a, int num_sms, cudaStream_t stream, con
         return cudaErrorInvalidValue;
       }
       return launch_any<256, EPI_SWIGLU>(a, num_sms, stream, err);
+    case EPI_LOGPROB:
+      *err = "gemm: EPI_LOGPROB needs target / partial buffers (CTA-pair kernel only)";
+      return cudaErrorInvalidValue;
     default:
       *err = "gemm: unknown epilogue";
       return cudaErrorInvalidValue;

@@ -14,6 +14,7 @@ enum GemmEpilogue : int {
   EPI_RESID = 1,   // x = [x +] acc + bias (fp32, in place); xb = bf16(x * norm_w); ssq partials
   EPI_QKV = 2,     // v = acc*rstd + bias; 2-D rotary on q,k heads; bf16 [M,3840]
   EPI_SWIGLU = 3,  // h = silu(g*rstd+bg) * (u*rstd+bu), gate/up interleaved per 256-column tile
+  EPI_LOGPROB = 4, // LM head without logits: per (row, 256-column block) max / sum-exp of acc * inv_temp, target logit
 };
 
 enum GemmFlags : int {
@@ -49,6 +50,12 @@ struct GemmArgs {
   float eps;
   const float* cos_tab;    // EPI_QKV: [M, 40] fp32
   const float* sin_tab;
+  // EPI_LOGPROB (CTA-pair kernel only): columns >= N are masked; partials are part-major [ceil(N/256)][M]
+  const int64_t* target;   // [M] column index whose scaled logit is wanted (out of range: none)
+  float inv_temp;          // 1 / temperature
+  float* part_max;         // [parts][M] max over the block of acc * inv_temp
+  float* part_sum;         // [parts][M] sum of exp(acc * inv_temp - max)
+  float* tgt_logit;        // [M] acc[target] * inv_temp
   // EPI_QKV, CTA-pair kernel: the same angles indexed by position (plan.cuh pos_win / pos_tab); optional — without
   // them (or with more than 64 positions) the single-CTA kernel runs with the per-row tables
   const int32_t* pos_win;  // [M] hpos | wpos << 16

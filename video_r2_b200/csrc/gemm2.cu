@@ -3,6 +3,8 @@
 //   EPI_QKV     C = xb * Wqkv^T      epilogue: * rstd(x), + bias, 2-D rotary on q,k, bf16           (N = 3840, BN = 240)
 //   EPI_RESID   C = A  * W^T         epilogue: x += C + bias (fp32), xb = bf16(x * w_norm), sum x^2  (N = 1280, BN = 256)
 //   EPI_SWIGLU  C = xb * Wgu^T       epilogue: * rstd, + bias, silu(gate) * up, bf16                 (N = 6912, BN = 256)
+//   EPI_LOGPROB C = h  * Wlm^T       epilogue: per-block max / sum-exp of C / T and the target logit: the LM head's
+//                                    per-token log-probabilities without materialising [M, vocab] logits
 //
 // Why a second kernel (ncu r01c, profiles/): in the single-CTA kernel (gemm.cu) the tensor core's operand reads
 // take 75 % of the SM's L1/shared data pipe at full rate (128 x 256 tile: 48 KB per 512 cycles) and the epilogue's
@@ -47,6 +49,12 @@ struct Cfg2<EPI_QKV, 0> {
   static constexpr int BN = 240, groups = 3, stages = 5;
   static constexpr int out_bytes = 6 * kBox;   // 3 heads x (first | second rotary half) boxes of 40 bf16 columns
   static constexpr int aux_bytes = kMaxPos * 160;   // cos | sin of every (h or w) position: [64][40] fp32
+};
+template <>
+struct Cfg2<EPI_LOGPROB, 0> {
+  static constexpr int BN = 256, groups = 4, stages = 6;
+  static constexpr int out_bytes = 0;
+  static constexpr int aux_bytes = 2 * 4 * 128 * 8;   // two item parities x 4 column groups x 128 rows x (max, sum)
 };
 template <>
 struct Cfg2<EPI_SWIGLU, 0> {
@@ -123,7 +131,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const bool leader = rank == 0;
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
-  const int num_n = p.N / BN;
+  const int num_n = (p.N + BN - 1) / BN;   // only EPI_LOGPROB may have a ragged last column block (masked)
   const int num_pair_m = (p.M + 2 * BM - 1) / (2 * BM);
   const int num_tiles = num_pair_m * num_n;
   const int num_k_blocks = (p.K + BK - 1) / BK;
@@ -298,6 +306,34 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         __syncwarp();
       }
+    } else if constexpr (EPI == EPI_LOGPROB) {
+      // combine the 4 column groups' (max, sum-exp) per row in a fixed order and write the block's partial,
+      // part-major; out_free[parity] tells the epilogue warps the slot may be rewritten
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++local) {
+        const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
+        const int n_blk = tile % num_n;
+        mbar_wait(&store_ready[0], local & 1u);
+        const float2* red = reinterpret_cast<const float2*>(aux_base) + (local & 1u) * 4 * 128;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int row = lane + 32 * k;
+          float mx = red[row].x;
+#pragma unroll
+          for (int g = 1; g < 4; ++g) mx = fmaxf(mx, red[g * 128 + row].x);
+          float sum = 0.f;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float2 v = red[g * 128 + row];
+            sum += v.y * (v.x == -INFINITY ? 0.f : __expf(v.x - mx));
+          }
+          if (m0 + row < p.M) {
+            p.part_max[static_cast<int64_t>(n_blk) * p.M + m0 + row] = mx;
+            p.part_sum[static_cast<int64_t>(n_blk) * p.M + m0 + row] = sum;
+          }
+        }
+        __syncwarp();
+        if (issuer) mbar_arrive(&out_free[local & 1u]);
+      }
     } else {  // EPI_SWIGLU
       for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++local) {
         const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
@@ -453,6 +489,50 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (lane == 0) {
           if (leader) mbar_arrive(&acc_empty[as]); else mbar_arrive_cluster(acc_empty_leader + as * 8);
         }
+      } else if constexpr (EPI == EPI_LOGPROB) {
+        // group cg owns 64 vocabulary columns of the block; thread = token row
+        int64_t tgt = -1;
+        if (valid) tgt = p.target[r];
+        mbar_wait_relaxed(&acc_full[as], use & 1u);
+        tc_fence_after();
+        const int c0 = n0 + cg * 64;                  // first vocabulary column of this warp's piece
+        float mx = -INFINITY, sum = 0.f;
+#pragma unroll
+        for (int piece = 0; piece < 2; ++piece) {
+          uint32_t v[32];
+          tmem_ld32(taddr + cg * 64 + piece * 32, v);
+          tmem_ld_wait();
+          const int cbase = c0 + piece * 32;
+          float pm = -INFINITY;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float sv = cbase + i < p.N ? __uint_as_float(v[i]) * p.inv_temp : -INFINITY;   // mask the ragged vocabulary tail
+            v[i] = __float_as_uint(sv);
+            pm = fmaxf(pm, sv);
+          }
+          if (tgt >= cbase && tgt < cbase + 32 && tgt < p.N) {   // at most one (block, group, piece) per row holds the target
+            float t = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t = (tgt - cbase == i) ? __uint_as_float(v[i]) : t;
+            p.tgt_logit[r] = t;
+          }
+          const float nm = fmaxf(mx, pm);
+          float ps = 0.f;
+          if (nm != -INFINITY) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ps += __expf(__uint_as_float(v[i]) - nm);
+            sum = sum * (mx == -INFINITY ? 0.f : __expf(mx - nm)) + ps;
+          }
+          mx = nm;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(&acc_empty[as]); else mbar_arrive_cluster(acc_empty_leader + as * 8);
+        }
+        // (max, sum) of this warp's 64 columns -> the item parity's slot; the store warp combines the 4 groups
+        if (use > 0) mbar_wait(&out_free[as], (use - 1) & 1u);   // the store warp has consumed this slot's previous item
+        reinterpret_cast<float2*>(aux_base)[(as * 4 + cg) * 128 + row] = make_float2(mx, sum);
       } else {  // EPI_SWIGLU
         // tile columns [0,128) are gate rows, [128,256) the matching up rows; group cg owns 32 outputs
         float rstd = 0.f;
@@ -530,6 +610,10 @@ cudaError_t launch2(const GemmArgs& a, int num_sms, cudaStream_t stream, const c
     ok = ok && tma_encode_2d_swz(&tm0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a.x, a.N, a.M, a.ldx * 4, 32, BM, 128) &&
          tma_encode_2d_swz(&tm1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.out_bf16, a.N, a.M, a.ld_out * 2, 32, BM, 64);
     tm2 = tm1;
+  } else if (EPI == EPI_LOGPROB) {
+    tm0 = tmA;
+    tm1 = tmA;
+    tm2 = tmA;
   } else {
     ok = ok && encode(&tm0, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.out_bf16, a.N / 2, a.M, a.ld_out * 2, 64, BM, true);
     tm1 = tm0;
@@ -563,7 +647,7 @@ cudaError_t launch2(const GemmArgs& a, int num_sms, cudaStream_t stream, const c
     }
     max_clusters = n < num_sms / 2 ? n : num_sms / 2;
   }
-  const int pair_tiles = ((a.M + 2 * BM - 1) / (2 * BM)) * (a.N / L::BN);
+  const int pair_tiles = ((a.M + 2 * BM - 1) / (2 * BM)) * ((a.N + L::BN - 1) / L::BN);
   int clusters = max_clusters;
   if (pair_tiles < clusters) clusters = pair_tiles;
   gemm2_kernel<EPI, V><<<2 * clusters, L::threads, L::smem_bytes, stream>>>(tmA, tmB, tm0, tm1, tm2, a);
@@ -578,6 +662,7 @@ bool gemm2_supports(const GemmArgs& a) {
     case EPI_QKV: return a.N % 240 == 0 && (a.N / 3) % 80 == 0 && a.pos_win != nullptr && a.pos_tab != nullptr && a.n_pos > 0 && a.n_pos <= kMaxPos;
     case EPI_RESID: return (a.flags & GEMM_ADD_RESID) != 0 && a.N % 256 == 0 && a.bias != nullptr;
     case EPI_SWIGLU: return a.N % 256 == 0;
+    case EPI_LOGPROB: return a.target != nullptr && a.part_max != nullptr && a.part_sum != nullptr && a.tgt_logit != nullptr;
     default: return false;
   }
 }
@@ -589,6 +674,7 @@ cudaError_t gemm2_launch(const GemmArgs& a, int num_sms, cudaStream_t stream, co
     case EPI_QKV: return launch2<EPI_QKV, 0>(a, num_sms, stream, err);
     case EPI_RESID: return launch2<EPI_RESID, 0>(a, num_sms, stream, err);
     case EPI_SWIGLU: return launch2<EPI_SWIGLU, 0>(a, num_sms, stream, err);
+    case EPI_LOGPROB: return launch2<EPI_LOGPROB, 0>(a, num_sms, stream, err);
     default: *err = "gemm2: unsupported epilogue"; return cudaErrorInvalidValue;
   }
 }
