@@ -358,13 +358,32 @@ def run_vr2(args, rank, local_rank, world):
                 next(res)
         pipe.drain()
 
+    # and from the decoder's frames at SOURCE resolution, [T,H,W,3] uint8 as decord hands them over: fetch_video's
+    # anti-aliased bicubic resize (vr2.resize_frames, byte-identical to torchvision on the CPU) also moves to the GPU
+    RAW = (720, 720)
+    raw_host = [torch.randint(0, 256, (frames_host[0].shape[0], RAW[0], RAW[1], 3), dtype=torch.uint8,
+                              generator=torch.Generator().manual_seed(17 + k)).pin_memory().permute(0, 3, 1, 2)
+                for k in range(2)] if frames_host is not None else None
+
+    def run_pipe_raw(steps):
+        res = pipe.results()
+        for i in range(steps):
+            pipe.submit_frames(raw_host[i % 2], size=(CLIP[1] * 14, CLIP[2] * 14), out_host=out_hosts[i % 2],
+                               input_ids_host=ids_host, video_grid_thw=vid_thw, second_per_grid_ts=spg,
+                               pos_host=pos_hosts[i % 2])
+            if i >= 1:
+                next(res)
+        pipe.drain()
+
     run_pipe(3)
     ms_e2e = timed_pipe(run_pipe, args.steps) / args.steps
     e2e_value = tokens_total / (ms_e2e * 1e-3)
-    ms_e2e_frames = None
+    ms_e2e_frames = ms_e2e_raw = None
     if frames_host is not None and world == 1:
         run_pipe_frames(3)
         ms_e2e_frames = timed_pipe(run_pipe_frames, args.steps) / args.steps
+        run_pipe_raw(3)
+        ms_e2e_raw = timed_pipe(run_pipe_raw, args.steps) / args.steps
     for i in range(2):
         step_e2e(i)
     ms_e2e_sync = timed(step_e2e, args.steps) / args.steps
@@ -486,7 +505,12 @@ def run_vr2(args, rank, local_rank, world):
                 "from_frames": None if ms_e2e_frames is None else {
                     "value": tokens_total / (ms_e2e_frames * 1e-3), "ms_per_step": ms_e2e_frames,
                     "h2d_bytes_per_step": int(frames_host[0].numel()) + ids_host.numel() * 8,
-                    "what": "uint8 frames [32,3,448,448] up, rescale+normalise+patchify on the GPU, then the same path"}},
+                    "what": "uint8 frames [32,3,448,448] up, rescale+normalise+patchify on the GPU, then the same path"},
+                "from_raw_frames": None if ms_e2e_raw is None else {
+                    "value": tokens_total / (ms_e2e_raw * 1e-3), "ms_per_step": ms_e2e_raw,
+                    "h2d_bytes_per_step": int(raw_host[0].numel()) + ids_host.numel() * 8,
+                    "what": "decoder frames [32,720,720,3] uint8 up, bicubic-antialias resize to 448x448 + "
+                            "rescale+normalise+patchify on the GPU, then the same path"}},
         "gpu_launches": launches * args.steps,
         "clocks": clocks,
         "breakdown_ms_per_step": {k: round(v[0] / 3, 4) for k, v in breakdown.items()},

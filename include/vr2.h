@@ -237,6 +237,20 @@ int vr2_patchify(const void* frames_dev, int32_t frames_dtype, int32_t T, int32_
                  const float* std_host, void* out_dev, int32_t out_dtype, void* stream);
 
 /* ------------------------------------------------------------------------
+ * Frame resize (before patchify): replaces the host-side
+ * `transforms.functional.resize(video, [h, w], BICUBIC, antialias=True)` of Video-R2's fetch_video
+ * (train/qwen_vl_utils/vision_process.py:802-807; same under demo/ and eval/).  frames_dev: uint8, element
+ * (t, c, y, x) at byte offset t*stride_t + c*stride_c + y*stride_h + x*stride_w (so [T,C,H,W] and the decoders'
+ * [T,H,W,C] are both accepted without a copy); out_dev: contiguous [T, C, out_h, out_w], uint8 (torchvision's result)
+ * or fp32 (the same values, as `.float()` returns them).  workspace_dev: vr2_resize_workspace_bytes() bytes, holds
+ * the two filter tables of this call.  T*C <= 65535 per call.  Byte-identical to torchvision 0.26 / torch 2.11 on
+ * the CPU (oracle/resize.py). */
+int vr2_resize_workspace_bytes(int32_t H, int32_t W, int32_t out_h, int32_t out_w, size_t* bytes);
+int vr2_resize_frames(const void* frames_dev, int32_t T, int32_t C, int32_t H, int32_t W, int64_t stride_t,
+                      int64_t stride_c, int64_t stride_h, int64_t stride_w, int32_t out_h, int32_t out_w, void* out_dev,
+                      int32_t out_dtype, void* workspace_dev, void* stream);
+
+/* ------------------------------------------------------------------------
  * Decoder-side M-RoPE application: the consumer of vr2_rope_index's position ids.
  * Replaces Qwen2_5_VLRotaryEmbedding.forward + apply_multimodal_rotary_pos_emb (transformers
  * modeling_qwen2_5_vl.py; Liger's liger_multimodal_rotary_pos_emb in train_sft.py:83-84) with one kernel that forms

@@ -134,7 +134,77 @@ def mrope_goldens():
     print("mrope", out["rq_bf16"].shape)
 
 
+RESIZE_CASES = {  # name: ((T, H, W), (h', w'), channels_last source, seed)
+    "down_90x160_to_56x84": ((2, 90, 160), (56, 84), False, 0),
+    "up_50x70_to_84x112": ((1, 50, 70), (84, 112), False, 1),
+    "hwc_72x128_to_28x56": ((3, 72, 128), (28, 56), True, 2),        # decord layout: [T,H,W,C] permuted to [T,C,H,W]
+    "steep_200x37_to_28x28": ((1, 200, 37), (28, 28), False, 3),     # 29 taps down, 5 taps sideways
+    "width_only_64x100_to_64x56": ((1, 64, 100), (64, 56), False, 4),
+}
+
+
+def resize_goldens():
+    """uint8 frames through the reference's own call (vision_process.py:802-807: torchvision tensor resize, bicubic,
+    antialias) plus the float32 result of F.interpolate before the rounding; and tables of the reference module's
+    smart_resize / smart_nframes (imported from /root/reference) over a sweep of arguments."""
+    import torch.nn.functional as F
+    from torchvision import transforms
+    from torchvision.transforms import InterpolationMode
+    for name, ((T, H, W), (oh, ow), hwc, seed) in RESIZE_CASES.items():
+        g = torch.Generator().manual_seed(seed)
+        if hwc:
+            v = torch.randint(0, 256, (T, H, W, 3), dtype=torch.uint8, generator=g).permute(0, 3, 1, 2)
+        else:
+            v = torch.randint(0, 256, (T, 3, H, W), dtype=torch.uint8, generator=g)
+        v[0, :, : H // 2] = (v[0, :, : H // 2].float() * 0.1 + 235).to(torch.uint8)   # a bright region: overshoot -> clamp at 255
+        out = transforms.functional.resize(v, [oh, ow], interpolation=InterpolationMode.BICUBIC, antialias=True)
+        raw = F.interpolate(v.float(), size=(oh, ow), mode="bicubic", antialias=True, align_corners=False)
+        assert out.dtype == torch.uint8 and torch.equal(out, raw.clamp(0, 255).round().to(torch.uint8))
+        np.savez_compressed(os.path.join(HERE, f"resize_{name}.npz"), frames=v.contiguous().numpy(), hwc=hwc, out=out.numpy(),
+                            raw=raw.contiguous().numpy())
+        print("resize", name, tuple(out.shape), "clamped", int((raw > 255).sum() + (raw < 0).sum()))
+    sys.path.insert(0, "/root/reference/train")
+    import qwen_vl_utils.vision_process as vp
+    rng = np.random.default_rng(0)
+    sizes, frames = [], []
+    for _ in range(300):
+        h, w = int(rng.integers(20, 2200)), int(rng.integers(20, 2200))
+        if max(h, w) / min(h, w) > 150:
+            continue
+        lo = int(rng.choice([4 * 28 * 28, 128 * 28 * 28, 256 * 28 * 28]))
+        hi = int(rng.choice([192 * 28 * 28, 151200, 768 * 28 * 28, 16384 * 28 * 28]))
+        if hi < lo:
+            continue
+        sizes.append([h, w, lo, hi, *vp.smart_resize(h, w, 28, lo, hi)])
+    for h, w in ((720, 1280), (1080, 1920), (360, 640), (480, 640), (14, 14), (28, 5000), (1000, 1014), (42, 70)):
+        sizes.append([h, w, vp.VIDEO_MIN_PIXELS, vp.VIDEO_MAX_PIXELS, *vp.smart_resize(h, w, 28, vp.VIDEO_MIN_PIXELS, vp.VIDEO_MAX_PIXELS)])
+    for _ in range(200):
+        total, vfps = int(rng.integers(2, 20000)), float(rng.choice([23.976, 24.0, 25.0, 29.97, 30.0, 60.0, 5.0]))
+        fps, mx = float(rng.choice([2.0, 1.0, 0.5, 4.0])), int(rng.choice([32, 128, 768, 7]))
+        try:
+            n = vp.smart_nframes({"fps": fps, "max_frames": min(mx, total)}, total, vfps)
+        except ValueError:
+            n = -1
+        frames.append([total, vfps, fps, min(mx, total), n])
+    for total, want in ((100, 7), (100, 8), (100, 9), (10, 10), (10, 12), (3, 2), (50, 1)):
+        try:
+            n = vp.smart_nframes({"nframes": want}, total, 30.0)
+        except ValueError:
+            n = -1
+        frames.append([total, 30.0, -1.0, want, n])
+    np.savez_compressed(os.path.join(HERE, "resize_helpers.npz"), sizes=np.asarray(sizes, dtype=np.int64),
+                        frames=np.asarray(frames, dtype=np.float64), fps_max_frames=vp.FPS_MAX_FRAMES,
+                        total_pixels=vp.VIDEO_TOTAL_PIXELS)
+    print("helpers", len(sizes), len(frames))
+
+
 if __name__ == "__main__":
-    main()
-    patchify_goldens()
-    mrope_goldens()
+    which = sys.argv[1:] or ["tower", "patchify", "mrope", "resize"]
+    if "tower" in which:
+        main()
+    if "patchify" in which:
+        patchify_goldens()
+    if "mrope" in which:
+        mrope_goldens()
+    if "resize" in which:
+        resize_goldens()

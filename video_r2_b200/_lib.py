@@ -86,6 +86,9 @@ SIGNATURES = {
     "vr2_scatter_rows": (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P, C.c_int64, C.c_int64, C.c_int64, _P]),
     "vr2_patchify": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                C.POINTER(C.c_float), C.POINTER(C.c_float), _P, C.c_int32, _P]),
+    "vr2_resize_workspace_bytes": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
+    "vr2_resize_frames": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                    C.c_int32, C.c_int32, _P, C.c_int32, _P, _P]),
     "vr2_mrope_apply": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P,
                                   C.POINTER(C.c_int32), C.c_float, _P]),
     "vr2_lm_logprob_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),

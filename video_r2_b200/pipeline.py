@@ -18,7 +18,7 @@ import collections
 
 import torch
 
-from .preprocess import patchify
+from .preprocess import patchify, resize_frames
 from .rope_index import get_rope_index
 
 
@@ -34,6 +34,7 @@ class HostPipeline:
         self.s_out = torch.cuda.Stream(self.dev)
         self._in = [None] * depth          # device pixel / frame buffers
         self._pix = [None] * depth         # device patch rows produced by patchify (submit_frames)
+        self._rsz = [None] * depth         # device frames after the resize (submit_frames(size=...))
         self._ids = [None] * depth
         self._out = [None] * depth         # device embedding buffers
         self._compute_done = [None] * depth
@@ -49,18 +50,21 @@ class HostPipeline:
         return b
 
     @torch.no_grad()
-    def submit_frames(self, frames_host: torch.Tensor, **kw):
-        """Like submit(), from resized uint8 (or fp32) frames [T, 3, H, W] in pinned host memory: the upload is 1 byte
-        per pixel value and rescale + normalise + patchify (the HF video processor's CPU work) run on the GPU
-        (`vr2.patchify`).  One clip per call; grid_thw is derived from the frame shape."""
+    def submit_frames(self, frames_host: torch.Tensor, size=None, **kw):
+        """Like submit(), from uint8 (or, already resized, fp32) frames [T, 3, H, W] in pinned host memory: the upload is
+        1 byte per pixel value; the resize (`size=(h', w')`: fetch_video's anti-aliased bicubic, `vr2.resize_frames`) and
+        rescale + normalise + patchify (the HF video processor's CPU work, `vr2.patchify`) run on the GPU.  A permuted
+        [T, H, W, 3] decoder buffer is accepted as is.  One clip per call; grid_thw is derived from the frame shape."""
         T, _, H, W = frames_host.shape
+        if size is not None:
+            H, W = int(size[0]), int(size[1])
         grid = [[-(-T // self.tower.cfg.temporal_patch_size), H // self.tower.cfg.patch_size, W // self.tower.cfg.patch_size]]
-        return self.submit(frames_host, grid, _frames=True, **kw)
+        return self.submit(frames_host, grid, _frames=True, _size=size, **kw)
 
     @torch.no_grad()
     def submit(self, x_host: torch.Tensor, grid_thw, out_host: torch.Tensor = None, input_ids_host: torch.Tensor = None,
                video_grid_thw=None, second_per_grid_ts=None, pos_host: torch.Tensor = None, out_dtype=None,
-               _frames: bool = False):
+               _frames: bool = False, _size=None):
         """Enqueue one batch.  `grid_thw` describes x_host's rows; when `input_ids_host` is given the M-RoPE position
         ids of that batch are computed too (`video_grid_thw` / `second_per_grid_ts`: device or host tensors)."""
         slot = self._n % self.depth
@@ -72,8 +76,15 @@ class HostPipeline:
         with torch.cuda.stream(self.s_in):
             if self._compute_done[slot] is not None:
                 self.s_in.wait_event(self._compute_done[slot])
-            x_dev = self._buf(self._in, slot, x_host.shape, x_host.dtype)
-            x_dev.copy_(x_host, non_blocking=True)
+            if x_host.dim() == 4 and not x_host.is_contiguous() and x_host.permute(0, 2, 3, 1).is_contiguous():
+                # decoder layout [T, H, W, C] viewed as [T, C, H, W]: upload the bytes as they lie, keep the view
+                hwc = x_host.permute(0, 2, 3, 1)
+                x_dev = self._buf(self._in, slot, hwc.shape, hwc.dtype)
+                x_dev.copy_(hwc, non_blocking=True)
+                x_dev = x_dev.permute(0, 3, 1, 2)
+            else:
+                x_dev = self._buf(self._in, slot, x_host.shape, x_host.dtype)
+                x_dev.copy_(x_host, non_blocking=True)
             ids_dev = None
             if input_ids_host is not None:
                 ids_dev = self._buf(self._ids, slot, input_ids_host.shape, input_ids_host.dtype)
@@ -88,6 +99,11 @@ class HostPipeline:
         if _frames:
             cfg = self.tower.cfg
             pix = self._buf(self._pix, slot, (plan.num_patches, cfg.patch_dim), torch.bfloat16)
+            if _size is not None:
+                rs = self._buf(self._rsz, slot, (x_dev.shape[0], x_dev.shape[1], int(_size[0]), int(_size[1])), torch.uint8)
+                x_dev = resize_frames(x_dev, _size, out=rs)
+            elif not x_dev.is_contiguous():
+                x_dev = x_dev.contiguous()
             patchify(x_dev, patch_size=cfg.patch_size, temporal_patch_size=cfg.temporal_patch_size,
                      merge_size=cfg.spatial_merge_size, out=pix)
             x_dev = pix
