@@ -46,6 +46,7 @@ typedef enum vr2_dtype {
   VR2_I64 = 2,
   VR2_I32 = 3,
   VR2_U8 = 4, /* also torch.bool */
+  VR2_F16 = 5, /* IEEE half: activations of VR2_PRECISION_F16 (single-operator test surface only) */
 } vr2_dtype;
 
 const char* vr2_last_error(void);
@@ -123,9 +124,16 @@ int vr2_tower_create(const vr2_tower_config* cfg, int32_t cuda_device, vr2_tower
  *                        bf16 path uses (modeling_qwen2_5_vl.py under autocast / .to(bfloat16)).
  *   VR2_PRECISION_SPLIT: every activation operand is carried as hi + lo bf16 (lo = rounding residual) and
  *                        multiplied twice (3 products inside attention): ~16 mantissa bits, 2x the MMA work.
- *                        This is the mode that meets max-abs 2e-2 against the fp32 reference on a 32-block tower.
+ *                        Meets max-abs 2e-2 against the fp32 reference on a 32-block tower.
+ *   VR2_PRECISION_F16:   activations (the operand of every contraction that is not a weight, the attention
+ *                        probabilities, q/k/v) are rounded to IEEE fp16 (11 significand bits) instead of bf16 (8);
+ *                        the GEMMs read fp16 copies of the bf16 weights (exact inside fp16's normal range; +1.35 GB,
+ *                        made on first use), the patch embedding still multiplies bf16 pixels by bf16 weights.  The
+ *                        work and the speed are those of VR2_PRECISION_BF16 with ~8x less operand rounding: also
+ *                        meets 2e-2.  Conversions saturate at +-65504 (fp16's range); a checkpoint whose
+ *                        activations exceed that needs BF16 or SPLIT.
  * Changes vr2_tower_workspace_bytes(); call before sizing the workspace. */
-typedef enum vr2_precision { VR2_PRECISION_BF16 = 0, VR2_PRECISION_SPLIT = 1 } vr2_precision;
+typedef enum vr2_precision { VR2_PRECISION_BF16 = 0, VR2_PRECISION_SPLIT = 1, VR2_PRECISION_F16 = 2 } vr2_precision;
 int vr2_tower_set_precision(vr2_tower* tower, int32_t precision);
 int32_t vr2_tower_get_precision(const vr2_tower* tower);
 void vr2_tower_destroy(vr2_tower* tower);
@@ -283,6 +291,10 @@ int vr2_op_linear(const void* a_dev, const void* w_dev, const float* bias_dev, v
 /* Split-operand variant: C = (A_hi + A_lo) W^T, A_lo bf16 with A's layout. */
 int vr2_op_linear_split(const void* a_hi_dev, const void* a_lo_dev, const void* w_dev, const float* bias_dev,
                         void* out_dev, int32_t out_dtype, int32_t M, int32_t N, int32_t K, int32_t gelu, void* stream);
+/* fp16 variant (VR2_PRECISION_F16): A and W fp16 (tcgen05 kind::f16 rejects mixed fp16 x bf16 operands — the tower
+ * keeps fp16 copies of its bf16 weights for this mode); out fp32, bf16 or fp16 (saturating at +-65504). */
+int vr2_op_linear_f16(const void* a_f16_dev, const void* w_dev, const float* bias_dev, void* out_dev, int32_t out_dtype,
+                      int32_t M, int32_t N, int32_t K, int32_t gelu, void* stream);
 /* out = bf16(x * rsqrt(mean(x^2)+eps) * w), x fp32 [rows, dim]. */
 int vr2_op_rmsnorm(const float* x_dev, const float* w_dev, void* out_bf16_dev, int64_t rows, int32_t dim, float eps,
                    void* stream);
@@ -290,6 +302,10 @@ int vr2_op_rmsnorm(const float* x_dev, const float* w_dev, void* out_bf16_dev, i
  * out bf16 [N, heads*80]. Synchronises the stream (test helper). */
 int vr2_op_attention(const void* qkv_dev, void* out_dev, const int32_t* cu_seqlens_host, int32_t n_seq,
                      int32_t num_heads, void* stream);
+
+/* fp16 variant (VR2_PRECISION_F16): qkv and out hold fp16. */
+int vr2_op_attention_f16(const void* qkv_f16_dev, void* out_f16_dev, const int32_t* cu_seqlens_host, int32_t n_seq,
+                         int32_t num_heads, void* stream);
 
 /* Split-operand variant: q/k/v and the output are hi + lo bf16 pairs of the same layout. */
 int vr2_op_attention_split(const void* qkv_hi_dev, const void* qkv_lo_dev, void* out_hi_dev, void* out_lo_dev,

@@ -103,3 +103,49 @@ def test_attention_split_matches_fp32(lens):
     err_plain = (ops.attention(hi, cu, heads).float() - _attn_ref(qkv32, cu, heads)).abs().max().item()
     print(f"\nsplit {err:.2e}  plain {err_plain:.2e}")
     assert err < 3e-4, err
+
+
+# ------------------------------------------------------------------ "f16" precision (fp16 activations x bf16 weights)
+@pytest.mark.parametrize("M,N,K", [(200, 288, 1176), (1000, 1280, 1280), (4096, 1280, 3456), (513, 3584, 5120)])
+def test_linear_f16_activations(M, N, K):
+    """tcgen05 kind::f16 with fp16 operands (the bf16 weight converts exactly): against fp64 of the same operands the
+    error is fp32 accumulation only; against the unrounded activations it is ~8x below the bf16 GEMM."""
+    from video_r2_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    a32 = torch.randn(M, K, generator=g).cuda()
+    w = _bf16((N, K), 12, scale=0.05)
+    a16 = a32.to(torch.float16)
+    w16 = w.to(torch.float16)
+    assert (w16.float() - w.float()).abs().max().item() <= 2.0 ** -25   # exact above 2^-14, subnormal grid below
+    out = ops.linear(a16, w16)
+    exact = (a16.double() @ w16.double().T).float()
+    assert (out - exact).abs().max().item() < 1e-3 * math.sqrt(K / 64)
+    ref = (a32.double() @ w.double().T).float()
+    e_f16 = (out - ref).abs().max().item()
+    e_bf16 = (ops.linear(a32.to(torch.bfloat16), w) - ref).abs().max().item()
+    print(f"\nf16 {e_f16:.2e}  bf16 {e_bf16:.2e}")
+    assert e_f16 * 4 < e_bf16
+    # fp16 output: round-to-nearest, saturating at the fp16 range instead of overflowing
+    o16 = ops.linear(a16, w16, out_dtype=torch.float16)
+    assert o16.dtype == torch.float16 and torch.equal(o16, out.to(torch.float16))
+    big = ops.linear((a16 * 0 + 60000).to(torch.float16), (w16 * 0 + 1).to(torch.float16), out_dtype=torch.float16)
+    assert torch.isfinite(big).all() and big.max().item() == 65504.0
+
+
+@pytest.mark.parametrize("lens", [[64] * 6, [4, 16, 64, 32, 8, 48, 12], [1008, 720], [100, 1, 63, 65, 129]])
+def test_attention_f16(lens):
+    from video_r2_b200 import ops
+    heads = 16
+    cu = [0]
+    for L in lens:
+        cu.append(cu[-1] + L)
+    g = torch.Generator().manual_seed(13)
+    qkv32 = torch.randn(cu[-1], 3 * heads * 80, generator=g).cuda()
+    q16 = qkv32.to(torch.float16)
+    out = ops.attention(q16, cu, heads)
+    assert out.dtype == torch.float16
+    ref = _attn_ref(q16.float(), cu, heads)
+    err = (out.float() - ref).abs().max().item()
+    err_bf16 = (ops.attention(qkv32.to(torch.bfloat16), cu, heads).float() - _attn_ref(qkv32.to(torch.bfloat16).float(), cu, heads)).abs().max().item()
+    print(f"\nf16 {err:.2e}  bf16 {err_bf16:.2e}")
+    assert err < 3e-3 and err * 4 < err_bf16, (err, err_bf16)

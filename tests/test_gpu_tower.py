@@ -4,6 +4,7 @@ Tolerance (BASELINE.json north_star): bf16 embeddings within max-abs 2e-2 and co
 the fp32 reference.  Two operand precisions exist (include/vr2.h vr2_precision):
   * "split" (hi + lo bf16 operands): asserted at max-abs <= 2e-2 AND cosine >= 0.9995 on every golden,
     including the depth-32 ragged one, with bf16 output — the north-star bound, met.
+  * "f16" (fp16 activations x bf16 weights, the speed of "bf16"): the same assertion, met.
   * "bf16" (the arithmetic HF's own bf16 path uses; the throughput mode): cosine >= 0.9995 asserted; max-abs
     is bounded by the operand-rounding floor SURVEY §7.3 measured for ANY bf16-operand implementation of a
     32-block tower on this init (0.06; HF's own bf16 path: 0.165), asserted at 8e-2 and printed."""
@@ -59,6 +60,29 @@ def test_tower_split_precision_meets_north_star_tolerance(path):
     assert e32 <= 5e-3, e32   # without the final bf16 rounding of a +-7 output (0.0156) the path is ~1e-3 or better
     # fp32 pixels take the split cast (hi + lo) path: same result for bf16-exact pixels
     assert torch.equal(tower(x.float().cuda(), grid), out32)
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "tower_*.npz"))), ids=os.path.basename)
+def test_tower_f16_precision_meets_north_star_tolerance(path):
+    """fp16 activations x bf16 weights: the speed of the bf16 mode, inside the north-star bound."""
+    g = np.load(path)
+    cfg = T.TowerConfig(depth=int(g["depth"]), fullatt_block_indexes=tuple(int(v) for v in g["fullatt"]))
+    w = T.make_weights(cfg, seed=int(g["weight_seed"]))
+    grid = g["grid"].tolist()
+    n = sum(t * h * ww for t, h, ww in grid)
+    x = torch.randn(n, 1176, generator=torch.Generator().manual_seed(int(g["pixel_seed"]))).to(torch.bfloat16)
+    tower = _tower(cfg, w, precision="f16")
+    ref = torch.from_numpy(g["out"])
+    out32 = tower(x.cuda(), grid, out_dtype=torch.float32)
+    out16 = tower(x.cuda(), grid)
+    assert out16.dtype == torch.bfloat16
+    e32, c32, r32 = _stats(out32, ref)
+    e16, c16, r16 = _stats(out16, ref)
+    print(f"\n{os.path.basename(path)} [f16]: fp32-out max-abs {e32:.5f} cos {c32:.7f} | bf16-out max-abs {e16:.5f} "
+          f"cos {c16:.7f} min-row-cos {r16:.7f}")
+    assert e16 <= TOL_MAX_ABS and c16 >= TOL_COSINE and r16 >= TOL_COSINE, (e16, c16, r16)
+    assert e32 <= 1.2e-2, e32
+    assert torch.equal(tower(x.cuda(), grid, out_dtype=torch.float32), out32)      # deterministic
 
 
 @pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "tower_*.npz"))), ids=os.path.basename)

@@ -8,9 +8,9 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvr2.so")
 
-VR2_F32, VR2_BF16, VR2_I64, VR2_I32, VR2_U8 = 0, 1, 2, 3, 4
-VR2_PRECISION_BF16, VR2_PRECISION_SPLIT = 0, 1
-PRECISIONS = {"bf16": VR2_PRECISION_BF16, "split": VR2_PRECISION_SPLIT}
+VR2_F32, VR2_BF16, VR2_I64, VR2_I32, VR2_U8, VR2_F16 = 0, 1, 2, 3, 4, 5
+VR2_PRECISION_BF16, VR2_PRECISION_SPLIT, VR2_PRECISION_F16 = 0, 1, 2
+PRECISIONS = {"bf16": VR2_PRECISION_BF16, "split": VR2_PRECISION_SPLIT, "f16": VR2_PRECISION_F16}
 
 
 class Vr2Error(RuntimeError):
@@ -100,9 +100,11 @@ SIGNATURES = {
     "vr2_rope_index": (C.c_int, [C.POINTER(RopeConfig), _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, _P,
                                  C.c_int32, _P, _P, _P, _P, _P]),
     "vr2_op_linear": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "vr2_op_linear_f16": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "vr2_op_linear_split": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "vr2_op_rmsnorm": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_float, _P]),
     "vr2_op_attention": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.c_int32, C.c_int32, _P]),
+    "vr2_op_attention_f16": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.c_int32, C.c_int32, _P]),
     "vr2_op_attention_split": (C.c_int, [_P, _P, _P, _P, C.POINTER(C.c_int32), C.c_int32, C.c_int32, _P]),
 }
 

@@ -105,6 +105,8 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 
 constexpr int kThreads = 320;   // 2 softmax warpgroups (one per stream) + producer warp + MMA warp
 
+// F16: q, k, v, the probabilities and the output are fp16 instead of bf16 (the f16 activation mode)
+template <int F16>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUtensorMap tm16,
                const __grid_constant__ CUtensorMap tmOut, const int2* __restrict__ seg, int n_rows, int num_heads,
@@ -218,9 +220,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
     // ------------------------------------------------------------ MMA issuer (whole warp; one elected lane issues)
     {
       const bool issuer = elect_one();
-      constexpr uint32_t id_s = idesc_bf16(TQ, TK, false);
-      constexpr uint32_t id_o64 = idesc_bf16(TQ, 64, true);
-      constexpr uint32_t id_o16 = idesc_bf16(TQ, 16, true);
+      constexpr uint32_t id_s = umma_idesc_fmt(idesc_bf16(TQ, TK, false), F16 != 0, F16 != 0);
+      constexpr uint32_t id_o64 = umma_idesc_fmt(idesc_bf16(TQ, 64, true), F16 != 0, F16 != 0);
+      constexpr uint32_t id_o16 = umma_idesc_fmt(idesc_bf16(TQ, 16, true), F16 != 0, F16 != 0);
       uint32_t it = 0;              // K|V ring position of the next block whose S has not been issued
       uint32_t nblk_done[2] = {0, 0};  // blocks of each stream whose S / P V have been issued (barrier phases)
       uint32_t npv_done[2] = {0, 0};
@@ -399,7 +401,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
               const float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), scale_log2, -m_scaled));
               rs0 += p0;
               rs1 += p1;
-              pk[i >> 1] = pack_bf16x2(p0, p1);
+              pk[i >> 1] = pack16x2<F16>(p0, p1);
             }
           } else {
 #pragma unroll
@@ -409,7 +411,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
               const float p1 = (c + 1 >= c_lo && c + 1 < c_hi) ? ex2_approx(fmaf(__uint_as_float(v[i + 1]), scale_log2, -m_scaled)) : 0.f;
               rs0 += p0;
               rs1 += p1;
-              pk[i >> 1] = pack_bf16x2(p0, p1);
+              pk[i >> 1] = pack16x2<F16>(p0, p1);
             }
           }
 #pragma unroll
@@ -441,8 +443,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
         for (int q = 0; q < 5; ++q) {
           const int i = half * 40 + q * 8;
           *reinterpret_cast<uint4*>(orow + half * (TQ * 80) + q * 16) =
-              make_uint4(pack_bf16x2(o[i] * inv, o[i + 1] * inv), pack_bf16x2(o[i + 2] * inv, o[i + 3] * inv),
-                         pack_bf16x2(o[i + 4] * inv, o[i + 5] * inv), pack_bf16x2(o[i + 6] * inv, o[i + 7] * inv));
+              make_uint4(pack16x2<F16>(o[i] * inv, o[i + 1] * inv), pack16x2<F16>(o[i + 2] * inv, o[i + 3] * inv),
+                         pack16x2<F16>(o[i + 4] * inv, o[i + 5] * inv), pack16x2<F16>(o[i + 6] * inv, o[i + 7] * inv));
         }
       }
       fence_proxy_async();
@@ -464,7 +466,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
 }  // namespace
 
 cudaError_t attention_tc_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, const int2* seg, int n_rows, int num_heads,
-                                int64_t ld_qkv, int64_t ld_out, int num_sms, cudaStream_t stream) {
+                                int64_t ld_qkv, int64_t ld_out, int num_sms, cudaStream_t stream, bool f16) {
   if (n_rows <= 0) return cudaSuccess;
   const int hidden = num_heads * HD;
   CUtensorMap tm64, tm16, tmOut;
@@ -475,13 +477,16 @@ cudaError_t attention_tc_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, co
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(attn_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(attn_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   });
   if (attr_err != cudaSuccess) return attr_err;
   const int items = ((n_rows + TQ - 1) / TQ) * num_heads;
   const int grid = items < num_sms ? items : num_sms;
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
-  attn_tc_kernel<<<grid, kThreads, SMEM_BYTES, stream>>>(tm64, tm16, tmOut, seg, n_rows, num_heads, hidden, scale_log2);
+  if (f16) attn_tc_kernel<1><<<grid, kThreads, SMEM_BYTES, stream>>>(tm64, tm16, tmOut, seg, n_rows, num_heads, hidden, scale_log2);
+  else attn_tc_kernel<0><<<grid, kThreads, SMEM_BYTES, stream>>>(tm64, tm16, tmOut, seg, n_rows, num_heads, hidden, scale_log2);
   return cudaGetLastError();
 }
 

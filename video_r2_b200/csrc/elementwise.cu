@@ -30,7 +30,7 @@ __global__ void cast_f32_bf16_kernel(const float4* __restrict__ src, uint2* __re
 // one warp per row; dim % 128 == 0 (32 lanes x float4)
 __global__ void rmsnorm_bf16_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                     __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_lo, int64_t rows,
-                                    int dim, float eps) {
+                                    int dim, float eps, bool f16) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
@@ -49,9 +49,14 @@ __global__ void rmsnorm_bf16_kernel(const float* __restrict__ x, const float* __
     for (int v = lane; v < dim / 4; v += 32) {
       const float4 a = xr[v];
       const float4 g = __ldg(reinterpret_cast<const float4*>(w) + v);
-      uint32_t h0, h1, l0, l1;
-      split_bf16x2(a.x * rstd * g.x, a.y * rstd * g.y, h0, l0);
-      split_bf16x2(a.z * rstd * g.z, a.w * rstd * g.w, h1, l1);
+      uint32_t h0, h1, l0 = 0, l1 = 0;
+      if (f16) {                                    // fp16 activations (never with out_lo)
+        h0 = pack_f16x2(a.x * rstd * g.x, a.y * rstd * g.y);
+        h1 = pack_f16x2(a.z * rstd * g.z, a.w * rstd * g.w);
+      } else {
+        split_bf16x2(a.x * rstd * g.x, a.y * rstd * g.y, h0, l0);
+        split_bf16x2(a.z * rstd * g.z, a.w * rstd * g.w, h1, l1);
+      }
       orow[v] = make_uint2(h0, h1);
       if (lrow != nullptr) lrow[v] = make_uint2(l0, l1);
     }
@@ -91,10 +96,27 @@ cudaError_t cast_f32_to_bf16(const float* src, __nv_bfloat16* dst, __nv_bfloat16
   return cudaGetLastError();
 }
 
+// bf16 -> fp16 (weights for the f16 activation mode: kind::f16 wants both operands in one format).  Exact for every
+// bf16 value inside fp16's normal range; below 2^-14 the value is rounded to fp16's subnormal grid (|error| <= 2^-25).
+__global__ void bf16_to_f16_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int64_t pairs) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < pairs;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint32_t v = src[i];
+    dst[i] = pack_f16x2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+  }
+}
+
+cudaError_t cast_bf16_to_f16(const __nv_bfloat16* src, void* dst, int64_t n, cudaStream_t stream) {
+  if (n % 2 != 0) return cudaErrorInvalidValue;
+  bf16_to_f16_kernel<<<grid_for(n / 2, 256), 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(src),
+                                                              static_cast<uint32_t*>(dst), n / 2);
+  return cudaGetLastError();
+}
+
 cudaError_t rmsnorm_to_bf16(const float* x, const float* w, __nv_bfloat16* out, __nv_bfloat16* out_lo, int64_t rows,
-                            int dim, float eps, cudaStream_t stream) {
-  if (dim % 4 != 0) return cudaErrorInvalidValue;
-  rmsnorm_bf16_kernel<<<grid_for(rows * 32, 256), 256, 0, stream>>>(x, w, out, out_lo, rows, dim, eps);
+                            int dim, float eps, cudaStream_t stream, bool f16) {
+  if (dim % 4 != 0 || (f16 && out_lo != nullptr)) return cudaErrorInvalidValue;
+  rmsnorm_bf16_kernel<<<grid_for(rows * 32, 256), 256, 0, stream>>>(x, w, out, out_lo, rows, dim, eps, f16);
   return cudaGetLastError();
 }
 

@@ -21,6 +21,8 @@ enum GemmFlags : int {
   GEMM_ADD_RESID = 1,  // EPI_RESID: read-modify-write x
   GEMM_GELU = 2,       // EPI_STORE: exact-erf GELU
   GEMM_OUT_F32 = 4,    // EPI_STORE: fp32 output (else bf16)
+  GEMM_A_F16 = 8,      // A and W hold fp16 (the f16 activation mode); kind::f16 rejects mixed fp16 x bf16 operands
+  GEMM_OUT_F16 = 16,   // the 16-bit output (out_bf16: EPI_STORE / xb / qkv / h) is written as fp16, saturating
 };
 
 struct GemmArgs {

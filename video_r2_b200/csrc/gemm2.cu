@@ -40,24 +40,24 @@ constexpr int kAccStride = 256;  // TMEM columns between the two accumulator sta
 constexpr int kMaxPos = 64;      // positions (patch rows / columns of one frame) the QKV kernel's rotary table holds
 constexpr int kBox = 128 * 80;   // one [128 rows x 80 bytes] epilogue box (20 fp32 or 40 bf16 columns)
 
-// V: reserved variant index (0 everywhere today).
+// V: format of the 16-bit output (and of the activations the epilogue produces): 0 bf16, 1 fp16 (GEMM_OUT_F16).
 template <int EPI, int V>
 struct Cfg2;
 
-template <>
-struct Cfg2<EPI_QKV, 0> {
+template <int V>
+struct Cfg2<EPI_QKV, V> {
   static constexpr int BN = 240, groups = 3, stages = 5;
   static constexpr int out_bytes = 6 * kBox;   // 3 heads x (first | second rotary half) boxes of 40 bf16 columns
   static constexpr int aux_bytes = kMaxPos * 160;   // cos | sin of every (h or w) position: [64][40] fp32
 };
-template <>
-struct Cfg2<EPI_LOGPROB, 0> {
+template <int V>
+struct Cfg2<EPI_LOGPROB, V> {
   static constexpr int BN = 256, groups = 4, stages = 6;
   static constexpr int out_bytes = 0;
   static constexpr int aux_bytes = 2 * 4 * 128 * 8;   // two item parities x 4 column groups x 128 rows x (max, sum)
 };
-template <>
-struct Cfg2<EPI_SWIGLU, 0> {
+template <int V>
+struct Cfg2<EPI_SWIGLU, V> {
   static constexpr int BN = 256, groups = 4, stages = 6;
   static constexpr int out_bytes = 2 * 16384;  // 128 x 128 bf16 as two 128B-swizzled 64-column boxes (single buffer: its
                                                // store drains long before the next tile's accumulator is complete)
@@ -74,8 +74,8 @@ constexpr int kSubX = 128 * 128;      // [128 rows x 32 fp32]
 constexpr int kSubXb = 128 * 64;      // [128 rows x 32 bf16]
 constexpr int kSubBytes = kSubX + kSubXb;
 constexpr int kResidBufs = 4;
-template <>
-struct Cfg2<EPI_RESID, 0> {
+template <int V>
+struct Cfg2<EPI_RESID, V> {
   static constexpr int BN = 256, groups = 4, stages = 4;
   static constexpr int out_bytes = kResidBufs * kSubBytes;
   static constexpr int aux_bytes = 4 * 128 * 4;          // per warp group partial sums of squares
@@ -196,7 +196,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------ MMA issuer (leader CTA; whole warp, one elected lane)
     if (leader) {
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN);
+      const uint32_t idesc = umma_idesc_fmt(umma_idesc_bf16(2 * BM, BN), (p.flags & GEMM_A_F16) != 0, (p.flags & GEMM_A_F16) != 0);
       uint32_t it = 0;
       uint32_t local = 0;
       for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++local) {
@@ -409,8 +409,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             f.w = __uint_as_float(v[4 * j + 3]) + bi.w + xo.w;
             ss = fmaf(f.x, f.x, ss); ss = fmaf(f.y, f.y, ss); ss = fmaf(f.z, f.z, ss); ss = fmaf(f.w, f.w, ss);
             *xp = f;                                                         // new residual, in place
-            pk[2 * j] = pack_bf16x2(f.x * w.x, f.y * w.y);                   // next GEMM's operand: x * w_norm
-            pk[2 * j + 1] = pack_bf16x2(f.z * w.z, f.w * w.w);
+            pk[2 * j] = pack16x2<V>(f.x * w.x, f.y * w.y);                   // next GEMM's operand: x * w_norm
+            pk[2 * j + 1] = pack16x2<V>(f.z * w.z, f.w * w.w);
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -480,9 +480,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
           }
           *reinterpret_cast<uint4*>(out_row + i0 * 2) =
-              make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
+              make_uint4(pack16x2<V>(a[0], a[1]), pack16x2<V>(a[2], a[3]), pack16x2<V>(a[4], a[5]), pack16x2<V>(a[6], a[7]));
           *reinterpret_cast<uint4*>(out_row + kBox + i0 * 2) =
-              make_uint4(pack_bf16x2(b[0], b[1]), pack_bf16x2(b[2], b[3]), pack_bf16x2(b[4], b[5]), pack_bf16x2(b[6], b[7]));
+              make_uint4(pack16x2<V>(b[0], b[1]), pack16x2<V>(b[2], b[3]), pack16x2<V>(b[4], b[5]), pack16x2<V>(b[6], b[7]));
         }
         tc_fence_before();
         __syncwarp();
@@ -565,9 +565,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           const int chunk = (cg & 1) * 4 + piece * 2;
           *reinterpret_cast<uint4*>(orow + (((chunk) ^ (row & 7)) << 4)) =
-              make_uint4(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]), pack_bf16x2(h[4], h[5]), pack_bf16x2(h[6], h[7]));
+              make_uint4(pack16x2<V>(h[0], h[1]), pack16x2<V>(h[2], h[3]), pack16x2<V>(h[4], h[5]), pack16x2<V>(h[6], h[7]));
           *reinterpret_cast<uint4*>(orow + (((chunk + 1) ^ (row & 7)) << 4)) =
-              make_uint4(pack_bf16x2(h[8], h[9]), pack_bf16x2(h[10], h[11]), pack_bf16x2(h[12], h[13]), pack_bf16x2(h[14], h[15]));
+              make_uint4(pack16x2<V>(h[8], h[9]), pack16x2<V>(h[10], h[11]), pack16x2<V>(h[12], h[13]), pack16x2<V>(h[14], h[15]));
         }
         tc_fence_before();
         __syncwarp();
@@ -670,10 +670,11 @@ bool gemm2_supports(const GemmArgs& a) {
 int gemm2_resid_parts(int n) { return n / 256; }
 
 cudaError_t gemm2_launch(const GemmArgs& a, int num_sms, cudaStream_t stream, const char** err) {
+  const bool f16 = (a.flags & GEMM_OUT_F16) != 0;
   switch (a.epilogue) {
-    case EPI_QKV: return launch2<EPI_QKV, 0>(a, num_sms, stream, err);
-    case EPI_RESID: return launch2<EPI_RESID, 0>(a, num_sms, stream, err);
-    case EPI_SWIGLU: return launch2<EPI_SWIGLU, 0>(a, num_sms, stream, err);
+    case EPI_QKV: return f16 ? launch2<EPI_QKV, 1>(a, num_sms, stream, err) : launch2<EPI_QKV, 0>(a, num_sms, stream, err);
+    case EPI_RESID: return f16 ? launch2<EPI_RESID, 1>(a, num_sms, stream, err) : launch2<EPI_RESID, 0>(a, num_sms, stream, err);
+    case EPI_SWIGLU: return f16 ? launch2<EPI_SWIGLU, 1>(a, num_sms, stream, err) : launch2<EPI_SWIGLU, 0>(a, num_sms, stream, err);
     case EPI_LOGPROB: return launch2<EPI_LOGPROB, 0>(a, num_sms, stream, err);
     default: *err = "gemm2: unsupported epilogue"; return cudaErrorInvalidValue;
   }

@@ -254,10 +254,30 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// A and/or B in fp16 instead of bf16 (F32F16 format field: 0 = F16, 1 = BF16; bits 7-9 for A, 10-12 for B)
+__host__ __device__ constexpr uint32_t umma_idesc_fmt(uint32_t idesc_bf16, bool a_f16, bool b_f16) {
+  return idesc_bf16 & ~((a_f16 ? 1u : 0u) << 7) & ~((b_f16 ? 1u : 0u) << 10);
+}
+
 // ---------------------------------------------------------------- small math
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+// fp16 pair, saturating at +-65504 instead of overflowing to infinity (the f16 activation mode)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// 16-bit activation pair in the format the next contraction reads: F16 = 0 bf16, 1 fp16
+template <int F16>
+__device__ __forceinline__ uint32_t pack16x2(float lo, float hi) {
+  if constexpr (F16) return pack_f16x2(lo, hi);
+  else return pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ uint32_t pack16x2_rt(float lo, float hi, bool f16) {
+  return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi);
 }
 // hi = bf16(v), lo = bf16(v - hi): the two-term operand split of the "precise" mode
 __device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {

@@ -46,6 +46,7 @@ struct Layer {
   Tensor gu_w, gu_b;              // bf16 [2*ipad, h] interleaved per 128, fp32 [2*ipad]
   bool gate_w_set = false, up_w_set = false, gate_b_set = false, up_b_set = false;
   Tensor down_w, down_b;          // bf16 [h, ipad], fp32 [h]
+  Tensor qkv_h, proj_h, gu_h, down_h;   // fp16 copies of the four matrices (VR2_PRECISION_F16), made on first use
 };
 
 }  // namespace
@@ -66,6 +67,8 @@ struct vr2_tower {
   vr2::Tensor lnq_w;               // fp32 [h]
   vr2::Tensor fc1_w, fc1_b;        // bf16 [md, md], fp32 [md]
   vr2::Tensor fc2_w, fc2_b;        // bf16 [out, md], fp32 [out]
+  vr2::Tensor fc1_h, fc2_h;        // fp16 copies (VR2_PRECISION_F16)
+  bool f16_ready = false;          // the fp16 copies reflect the current weights
   std::vector<void*> allocs;
   // optional per-kind CUDA-event timing (vr2_tower_profile)
   uint32_t prof_mask = 0;
@@ -91,6 +94,35 @@ bool is_full_layer(const vr2_tower* t, int l) {
   for (int i = 0; i < t->cfg.n_fullatt; ++i)
     if (t->cfg.fullatt_block_indexes[i] == l) return true;
   return false;
+}
+
+// fp16 copies of the GEMM weights, converted on the forward's stream the first time the f16 mode runs (and again after
+// a weight changes).  tcgen05 kind::f16 rejects mixed fp16 x bf16 operands (illegal instruction), so the f16
+// activation mode needs fp16 weights; bf16 -> fp16 is exact inside fp16's normal range.
+int ensure_f16_weights(vr2_tower* t, cudaStream_t s) {
+  if (t->f16_ready) return VR2_OK;
+  const size_t h = t->cfg.hidden_size, ip = t->ipad, md = t->merge_dim, oh = t->cfg.out_hidden_size;
+  auto conv = [&](const Tensor& src, Tensor* dst, size_t n) -> int {
+    if (dst->ptr == nullptr) {
+      void* p = nullptr;
+      VR2_CUDA(cudaMalloc(&p, n * 2));
+      t->allocs.push_back(p);
+      dst->ptr = p;
+    }
+    VR2_CUDA(cast_bf16_to_f16(static_cast<const __nv_bfloat16*>(src.ptr), dst->ptr, static_cast<int64_t>(n), s));
+    return VR2_OK;
+  };
+  int rc;
+  if ((rc = conv(t->fc1_w, &t->fc1_h, md * md)) != VR2_OK) return rc;
+  if ((rc = conv(t->fc2_w, &t->fc2_h, oh * md)) != VR2_OK) return rc;
+  for (auto& L : t->layers) {
+    if ((rc = conv(L.qkv_w, &L.qkv_h, 3 * h * h)) != VR2_OK) return rc;
+    if ((rc = conv(L.proj_w, &L.proj_h, h * h)) != VR2_OK) return rc;
+    if ((rc = conv(L.gu_w, &L.gu_h, 2 * ip * h)) != VR2_OK) return rc;
+    if ((rc = conv(L.down_w, &L.down_h, h * ip)) != VR2_OK) return rc;
+  }
+  t->f16_ready = true;
+  return VR2_OK;
 }
 
 constexpr size_t kMaxProfPairs = 8192;
@@ -198,6 +230,7 @@ extern "C" int vr2_tower_set_weight(vr2_tower* t, const char* name, const void* 
                                     const int64_t* shape, int32_t ndim, void* stream_v) {
   if (t == nullptr || name == nullptr || data == nullptr || shape == nullptr)
     return fail(VR2_ERR_ARG, "vr2_tower_set_weight: null argument");
+  t->f16_ready = false;
   if (dtype != VR2_F32 && dtype != VR2_BF16)
     return fail(VR2_ERR_ARG, "vr2_tower_set_weight(%s): dtype %d unsupported (fp32/bf16)", name, dtype);
   cudaStream_t s = as_stream(stream_v);
@@ -382,7 +415,15 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
   int rc;
 
   // ---- patch embed (Conv3d with kernel == stride == a [N,1176] x [1176,1280] GEMM), stored window-permuted
+  int rc0 = VR2_OK;
   const bool split = t->precision == VR2_PRECISION_SPLIT;
+  // f16 activation mode: every 16-bit activation buffer (xb, qkv, att, h, the merger's intermediates) holds fp16 instead
+  // of bf16 and the GEMMs read fp16 copies of the weights (ensure_f16_weights); the patch-embed GEMM multiplies the
+  // caller's bf16 pixels with the bf16 weight as before
+  const bool f16 = t->precision == VR2_PRECISION_F16;
+  const int act_in = f16 ? GEMM_A_F16 : 0, act_out = f16 ? GEMM_OUT_F16 : 0;
+  if (f16 && (rc0 = ensure_f16_weights(t, s)) != VR2_OK) return rc0;
+  auto WT = [&](const Tensor& w_bf16, const Tensor& w_f16) { return static_cast<const __nv_bfloat16*>(f16 ? w_f16.ptr : w_bf16.ptr); };
   const __nv_bfloat16* pix = static_cast<const __nv_bfloat16*>(pixels);
   if (pixels_dtype == VR2_F32) {
     ProfScope prof(t, VR2_K_CAST, s);
@@ -395,7 +436,7 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
     GemmArgs a{};
     a.A = pix; a.A_lo = w.pix_lo; a.lda = t->patch_k; a.W = static_cast<const __nv_bfloat16*>(t->patch_w.ptr); a.ldw = t->patch_k;
     a.M = static_cast<int>(N); a.N = h; a.K = t->patch_k;
-    a.epilogue = EPI_RESID; a.flags = 0;
+    a.epilogue = EPI_RESID; a.flags = act_out;
     a.x = w.x; a.ldx = h; a.out_bf16 = w.xb; a.out_lo = w.xb_lo; a.ld_out = h;
     a.row_map = plan->row_map;
     a.norm_w = static_cast<const float*>(t->layers[0].norm1_w.ptr);
@@ -407,9 +448,9 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
     const Layer& L = t->layers[l];
     {
       GemmArgs a{};
-      a.A = w.xb; a.A_lo = w.xb_lo; a.lda = h; a.W = static_cast<const __nv_bfloat16*>(L.qkv_w.ptr); a.ldw = h;
+      a.A = w.xb; a.A_lo = w.xb_lo; a.lda = h; a.W = WT(L.qkv_w, L.qkv_h); a.ldw = h;
       a.M = static_cast<int>(N); a.N = 3 * h; a.K = h;
-      a.epilogue = EPI_QKV;
+      a.epilogue = EPI_QKV; a.flags = act_in | act_out;
       a.bias = static_cast<const float*>(L.qkv_b.ptr);
       a.out_bf16 = w.qkv; a.out_lo = w.qkv_lo; a.ld_out = 3 * h;
       a.ssq_in = w.ssq; a.ssq_parts = parts; a.inv_dim = 1.0f / h; a.eps = eps;
@@ -426,13 +467,13 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
                                   3 * h, h, s));
       else
         VR2_CUDA(attention_tc_launch(w.qkv, w.att, full ? plan->seg_full : plan->seg_window, static_cast<int>(N),
-                                     t->cfg.num_heads, 3 * h, h, t->num_sms, s));
+                                     t->cfg.num_heads, 3 * h, h, t->num_sms, s, f16));
     }
     {
       GemmArgs a{};
-      a.A = w.att; a.A_lo = w.att_lo; a.lda = h; a.W = static_cast<const __nv_bfloat16*>(L.proj_w.ptr); a.ldw = h;
+      a.A = w.att; a.A_lo = w.att_lo; a.lda = h; a.W = WT(L.proj_w, L.proj_h); a.ldw = h;
       a.M = static_cast<int>(N); a.N = h; a.K = h;
-      a.epilogue = EPI_RESID; a.flags = GEMM_ADD_RESID;
+      a.epilogue = EPI_RESID; a.flags = GEMM_ADD_RESID | act_in | act_out;
       a.bias = static_cast<const float*>(L.proj_b.ptr);
       a.x = w.x; a.ldx = h; a.out_bf16 = w.xb; a.out_lo = w.xb_lo; a.ld_out = h;
       a.norm_w = static_cast<const float*>(L.norm2_w.ptr);
@@ -441,9 +482,9 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
     }
     {
       GemmArgs a{};
-      a.A = w.xb; a.A_lo = w.xb_lo; a.lda = h; a.W = static_cast<const __nv_bfloat16*>(L.gu_w.ptr); a.ldw = h;
+      a.A = w.xb; a.A_lo = w.xb_lo; a.lda = h; a.W = WT(L.gu_w, L.gu_h); a.ldw = h;
       a.M = static_cast<int>(N); a.N = 2 * t->ipad; a.K = h;
-      a.epilogue = EPI_SWIGLU;
+      a.epilogue = EPI_SWIGLU; a.flags = act_in | act_out;
       a.bias = static_cast<const float*>(L.gu_b.ptr);
       a.out_bf16 = w.hbuf; a.out_lo = w.hbuf_lo; a.ld_out = t->ipad;
       a.ssq_in = w.ssq; a.ssq_parts = parts; a.inv_dim = 1.0f / h; a.eps = eps;
@@ -451,9 +492,9 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
     }
     {
       GemmArgs a{};
-      a.A = w.hbuf; a.A_lo = w.hbuf_lo; a.lda = t->ipad; a.W = static_cast<const __nv_bfloat16*>(L.down_w.ptr); a.ldw = t->ipad;
+      a.A = w.hbuf; a.A_lo = w.hbuf_lo; a.lda = t->ipad; a.W = WT(L.down_w, L.down_h); a.ldw = t->ipad;
       a.M = static_cast<int>(N); a.N = h; a.K = t->ipad;
-      a.epilogue = EPI_RESID; a.flags = GEMM_ADD_RESID;
+      a.epilogue = EPI_RESID; a.flags = GEMM_ADD_RESID | act_in | act_out;
       a.bias = static_cast<const float*>(L.down_b.ptr);
       a.x = w.x; a.ldx = h; a.out_bf16 = w.xb; a.out_lo = w.xb_lo; a.ld_out = h;
       a.norm_w = static_cast<const float*>(l + 1 < t->cfg.depth ? t->layers[l + 1].norm1_w.ptr : t->lnq_w.ptr);
@@ -467,22 +508,22 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
   const int md = t->merge_dim;
   {
     ProfScope prof(t, VR2_K_MERGER_NORM, s);
-    VR2_CUDA(rmsnorm_to_bf16(w.x, static_cast<const float*>(t->lnq_w.ptr), w.qkv, w.qkv_lo, N, h, eps, s));
+    VR2_CUDA(rmsnorm_to_bf16(w.x, static_cast<const float*>(t->lnq_w.ptr), w.qkv, w.qkv_lo, N, h, eps, s, f16));
   }
   {
     GemmArgs a{};
-    a.A = w.qkv; a.A_lo = w.qkv_lo; a.lda = md; a.W = static_cast<const __nv_bfloat16*>(t->fc1_w.ptr); a.ldw = md;
+    a.A = w.qkv; a.A_lo = w.qkv_lo; a.lda = md; a.W = WT(t->fc1_w, t->fc1_h); a.ldw = md;
     a.M = static_cast<int>(T); a.N = md; a.K = md;
-    a.epilogue = EPI_STORE; a.flags = GEMM_GELU;
+    a.epilogue = EPI_STORE; a.flags = GEMM_GELU | act_in | act_out;
     a.bias = static_cast<const float*>(t->fc1_b.ptr);
     a.out_bf16 = w.hbuf; a.out_lo = w.hbuf_lo; a.ld_out = md;
     if ((rc = G(a, VR2_K_FC1, "merger.fc1")) != VR2_OK) return rc;
   }
   {
     GemmArgs a{};
-    a.A = w.hbuf; a.A_lo = w.hbuf_lo; a.lda = md; a.W = static_cast<const __nv_bfloat16*>(t->fc2_w.ptr); a.ldw = md;
+    a.A = w.hbuf; a.A_lo = w.hbuf_lo; a.lda = md; a.W = WT(t->fc2_w, t->fc2_h); a.ldw = md;
     a.M = static_cast<int>(T); a.N = t->cfg.out_hidden_size; a.K = md;
-    a.epilogue = EPI_STORE; a.flags = out_dtype == VR2_F32 ? GEMM_OUT_F32 : 0;
+    a.epilogue = EPI_STORE; a.flags = (out_dtype == VR2_F32 ? GEMM_OUT_F32 : 0) | act_in;   // the result itself: bf16 / fp32
     a.bias = static_cast<const float*>(t->fc2_b.ptr);
     a.out_bf16 = static_cast<__nv_bfloat16*>(out); a.out_f32 = static_cast<float*>(out);
     a.ld_out = t->cfg.out_hidden_size;
@@ -514,7 +555,7 @@ extern "C" int vr2_tower_forward_scatter(vr2_tower* t, const vr2_plan* plan, con
 
 extern "C" int vr2_tower_set_precision(vr2_tower* t, int32_t precision) {
   if (t == nullptr) return fail(VR2_ERR_ARG, "vr2_tower_set_precision: null tower");
-  if (precision != VR2_PRECISION_BF16 && precision != VR2_PRECISION_SPLIT)
+  if (precision != VR2_PRECISION_BF16 && precision != VR2_PRECISION_SPLIT && precision != VR2_PRECISION_F16)
     return fail(VR2_ERR_ARG, "vr2_tower_set_precision: unknown precision %d", precision);
   t->precision = precision;
   return VR2_OK;
@@ -546,7 +587,13 @@ extern "C" int vr2_tower_profile_read(vr2_tower* t, double* ms_by_kind, int64_t*
 
 // ----------------------------------------------------------------- single operators (test surface)
 static int op_linear_impl(const void* a_dev, const void* a_lo_dev, const void* w_dev, const float* bias, void* out,
-                          int32_t out_dtype, int32_t M, int32_t N, int32_t K, int32_t gelu, void* stream_v);
+                          int32_t out_dtype, int32_t M, int32_t N, int32_t K, int32_t gelu, void* stream_v,
+                          bool a_f16 = false);
+
+extern "C" int vr2_op_linear_f16(const void* a_dev, const void* w_dev, const float* bias, void* out, int32_t out_dtype,
+                                 int32_t M, int32_t N, int32_t K, int32_t gelu, void* stream_v) {
+  return op_linear_impl(a_dev, nullptr, w_dev, bias, out, out_dtype, M, N, K, gelu, stream_v, true);
+}
 
 extern "C" int vr2_op_linear(const void* a_dev, const void* w_dev, const float* bias, void* out, int32_t out_dtype,
                              int32_t M, int32_t N, int32_t K, int32_t gelu, void* stream_v) {
@@ -561,9 +608,10 @@ extern "C" int vr2_op_linear_split(const void* a_hi_dev, const void* a_lo_dev, c
 }
 
 static int op_linear_impl(const void* a_dev, const void* a_lo_dev, const void* w_dev, const float* bias, void* out,
-                          int32_t out_dtype, int32_t M, int32_t N, int32_t K, int32_t gelu, void* stream_v) {
+                          int32_t out_dtype, int32_t M, int32_t N, int32_t K, int32_t gelu, void* stream_v, bool a_f16) {
   if (a_dev == nullptr || w_dev == nullptr || out == nullptr) return fail(VR2_ERR_ARG, "vr2_op_linear: null pointer");
-  if (out_dtype != VR2_F32 && out_dtype != VR2_BF16) return fail(VR2_ERR_ARG, "vr2_op_linear: out dtype");
+  if (out_dtype != VR2_F32 && out_dtype != VR2_BF16 && !(a_f16 && out_dtype == VR2_F16))
+    return fail(VR2_ERR_ARG, "vr2_op_linear: out dtype");
   if (K % 8 != 0) return fail(VR2_ERR_ARG, "vr2_op_linear: K %% 8 != 0 (rows must be 16-byte aligned)");
   int dev = 0, sms = 148;
   VR2_CUDA(cudaGetDevice(&dev));
@@ -574,7 +622,8 @@ static int op_linear_impl(const void* a_dev, const void* a_lo_dev, const void* w
   a.W = static_cast<const __nv_bfloat16*>(w_dev); a.ldw = K;
   a.M = M; a.N = N; a.K = K;
   a.epilogue = EPI_STORE;
-  a.flags = (gelu ? GEMM_GELU : 0) | (out_dtype == VR2_F32 ? GEMM_OUT_F32 : 0);
+  a.flags = (gelu ? GEMM_GELU : 0) | (out_dtype == VR2_F32 ? GEMM_OUT_F32 : 0) | (a_f16 ? GEMM_A_F16 : 0) |
+            (out_dtype == VR2_F16 ? GEMM_OUT_F16 : 0);
   a.bias = bias;
   a.out_bf16 = static_cast<__nv_bfloat16*>(out); a.out_f32 = static_cast<float*>(out); a.ld_out = N;
   const char* msg = "";
@@ -592,7 +641,12 @@ extern "C" int vr2_op_rmsnorm(const float* x, const float* w, void* out, int64_t
 }
 
 static int op_attention_impl(const void* qkv, const void* qkv_lo, void* out, void* out_lo, const int32_t* cu,
-                             int32_t n_seq, int32_t num_heads, void* stream_v);
+                             int32_t n_seq, int32_t num_heads, void* stream_v, bool f16 = false);
+
+extern "C" int vr2_op_attention_f16(const void* qkv, void* out, const int32_t* cu, int32_t n_seq, int32_t num_heads,
+                                    void* stream_v) {
+  return op_attention_impl(qkv, nullptr, out, nullptr, cu, n_seq, num_heads, stream_v, true);
+}
 
 extern "C" int vr2_op_attention(const void* qkv, void* out, const int32_t* cu, int32_t n_seq, int32_t num_heads,
                                 void* stream_v) {
@@ -606,7 +660,7 @@ extern "C" int vr2_op_attention_split(const void* qkv_hi, const void* qkv_lo, vo
 }
 
 static int op_attention_impl(const void* qkv, const void* qkv_lo, void* out, void* out_lo, const int32_t* cu,
-                             int32_t n_seq, int32_t num_heads, void* stream_v) {
+                             int32_t n_seq, int32_t num_heads, void* stream_v, bool f16) {
   if (qkv == nullptr || out == nullptr || cu == nullptr || n_seq <= 0) return fail(VR2_ERR_ARG, "vr2_op_attention: null pointer");
   for (int i = 0; i < n_seq; ++i)
     if (cu[i + 1] < cu[i]) return fail(VR2_ERR_ARG, "vr2_op_attention: cu_seqlens not monotone");
@@ -628,7 +682,7 @@ static int op_attention_impl(const void* qkv, const void* qkv_lo, void* out, voi
     e = cudaMemcpyAsync(d, seg.data(), seg.size() * 8, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess)
       e = attention_tc_launch(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out),
-                              static_cast<const int2*>(d), n_rows, num_heads, 3 * num_heads * 80, num_heads * 80, sms, s);
+                              static_cast<const int2*>(d), n_rows, num_heads, 3 * num_heads * 80, num_heads * 80, sms, s, f16);
   } else {
     std::vector<int4> tiles;
     for (int i = 0; i < n_seq; ++i) {

@@ -154,9 +154,10 @@ class VisionTower:
     ("patch_embed.proj.weight", "blocks.0.attn.qkv.weight", ...), fp32 or bf16, any device."""
 
     def __init__(self, cfg: VisionConfig, state_dict, device="cuda:0", plan_cache: int = 16, precision=None):
-        """precision: "bf16" (default; activations rounded to bf16 once per GEMM input, as HF's bf16 path)
-        or "split" (hi + lo bf16 operands, ~16 mantissa bits, 2x the MMA work — the mode that meets
-        max-abs 2e-2 against the fp32 reference).  Default comes from $VR2_PRECISION."""
+        """precision: "bf16" (default; activations rounded to bf16 once per GEMM input, as HF's bf16 path),
+        "f16" (activations rounded to fp16 instead — 8x finer, same speed, fp16 copies of the weights (+1.35 GB);
+        meets max-abs 2e-2 against the fp32 reference; saturates at +-65504) or "split" (hi + lo bf16 operands, ~16 mantissa bits,
+        2x the MMA work; also meets 2e-2, no range limit).  Default comes from $VR2_PRECISION."""
         self.cfg = cfg
         self.device = torch.device(device)
         if self.device.type != "cuda":
