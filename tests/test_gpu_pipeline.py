@@ -45,3 +45,26 @@ def test_host_pipeline_from_uint8_frames_matches_processor_then_tower():
         rows, grid = P.patchify(c.numpy(), vr2.preprocess.OPENAI_CLIP_MEAN, vr2.preprocess.OPENAI_CLIP_STD)
         ref = tower(torch.from_numpy(rows).to(torch.bfloat16).cuda(), [grid])     # the reference's path: processor, cast, tower
         assert torch.equal(emb, ref.cpu())
+
+
+def test_host_pipeline_from_decoder_frames_resizes_on_the_gpu():
+    """[T,H,W,3] decoder buffers at source resolution: upload as they lie, fetch_video's resize + the processor on the GPU."""
+    import video_r2_b200 as vr2
+    from oracle import patchify as P
+    from oracle import resize as R
+    cfg_o = T.TowerConfig(depth=2, fullatt_block_indexes=(1,))
+    tower = vr2.VisionTower(vr2.VisionConfig(depth=2, fullatt_block_indexes=(1,)), T.make_weights(cfg_o, seed=2), device="cuda:0")
+    pipe = vr2.HostPipeline(tower, depth=2)
+    shapes = [(4, 90, 160), (2, 200, 120), (4, 90, 160)]
+    clips = [torch.randint(0, 256, (t, h, w, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(k)).pin_memory()
+             .permute(0, 3, 1, 2) for k, (t, h, w) in enumerate(shapes)]
+    sizes = [vr2.smart_resize(h, w, 28, 4 * 28 * 28, 12 * 28 * 28) for _, h, w in shapes]
+    for c, sz in zip(clips, sizes):
+        assert not c.is_contiguous()
+        pipe.submit_frames(c, size=sz)
+    got = pipe.drain()
+    for (emb, _), c, sz in zip(got, clips, sizes):
+        frames = R.resize_frames(c.contiguous().numpy(), *sz)
+        rows, grid = P.patchify(frames, vr2.preprocess.OPENAI_CLIP_MEAN, vr2.preprocess.OPENAI_CLIP_STD)
+        ref = tower(torch.from_numpy(rows).to(torch.bfloat16).cuda(), [grid])
+        assert emb.shape == ref.shape and torch.equal(emb, ref.cpu())
