@@ -170,7 +170,7 @@ def run_reference(args, rank):
         return
     kind, run = cpu_reference_runner()
     t1 = run(1)  # also the first warm-up
-    budget = 150.0
+    budget = float(os.environ.get("VR2_BENCH_REF_BUDGET_S", "150"))   # seconds of CPU work for the whole run
     slices = max(1, min(CLIP[0], int(budget / max(1e-3, (args.steps + args.warmup) * t1))))
     for _ in range(max(0, args.warmup - 1)):
         run(slices)
