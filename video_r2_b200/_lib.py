@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvr2.so")
+LIB_PATH = os.environ.get("VR2_LIB") or os.path.join(_HERE, "libvr2.so")   # VR2_LIB: an alternative build (A/B timing)
 
 VR2_F32, VR2_BF16, VR2_I64, VR2_I32, VR2_U8, VR2_F16 = 0, 1, 2, 3, 4, 5
 VR2_PRECISION_BF16, VR2_PRECISION_SPLIT, VR2_PRECISION_F16 = 0, 1, 2

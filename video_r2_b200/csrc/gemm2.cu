@@ -135,12 +135,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int num_pair_m = (p.M + 2 * BM - 1) / (2 * BM);
   const int num_tiles = num_pair_m * num_n;
   const int num_k_blocks = (p.K + BK - 1) / BK;
-  // QKV walks a contiguous range of tiles (same rows for up to 16 consecutive tiles: the cos/sin rows are loaded
-  // once per row block); the other two interleave clusters over tiles (n fastest: co-resident clusters share W and
-  // an A band in L2).
-  const int tile_begin = EPI == EPI_QKV ? static_cast<int>(static_cast<int64_t>(cluster_id) * num_tiles / num_clusters) : cluster_id;
-  const int tile_end = EPI == EPI_QKV ? static_cast<int>(static_cast<int64_t>(cluster_id + 1) * num_tiles / num_clusters) : num_tiles;
-  const int tile_step = EPI == EPI_QKV ? 1 : num_clusters;
+  // Clusters interleave over the tiles, n fastest: the 74 co-resident pairs then work on ~5 row blocks x all column
+  // blocks at a time, so each A box is wanted by up to num_n pairs and each W box by ~5 within a short window and L2
+  // serves them from one read (the L2 slices cap at ~6.3 KB/clk chip-wide; 74 pairs x 62 KB per k-block un-merged is
+  // 730 cycles against 480-512 of MMA).  QKV used to walk a contiguous range per pair (one row block at a time, a
+  // left-over of the per-row cos/sin loads): every pair then streamed its own A rows and the ring ran dry.
+  const int tile_begin = cluster_id;
+  const int tile_end = num_tiles;
+  const int tile_step = num_clusters;
 
   constexpr int kProducerWarp = E, kMmaWarp = E + 1, kStoreWarp = E + 2;
   if (warp == kProducerWarp && lane == 0) {
