@@ -48,6 +48,19 @@ def test_patched_visual_forward_matches_unpatched_hf():
         assert dummy.shape == (196, 3584) and torch.isfinite(dummy.float()).all()
     finally:
         vr2.uninstall()
+    # the same through install(precision="f16"): the tower is rebuilt in that mode and lands closer to the fp32 path
+    vr2.refresh(m)
+    vr2.install(precision="f16")
+    try:
+        out_h = m(x, grid_thw=grid)
+        out_h = out_h.pooler_output if hasattr(out_h, "pooler_output") else out_h
+        assert m.__dict__["_vr2_tower"].precision == "f16"
+        assert (out_h.float() - ref).abs().max().item() < 2e-2
+    finally:
+        vr2.uninstall()
+        vr2.install(precision=None)
+        vr2.uninstall()
+        vr2.refresh(m)
     with torch.no_grad():
         again = m(x.float(), grid_thw=grid)
     again = again.pooler_output if hasattr(again, "pooler_output") else again

@@ -27,6 +27,7 @@ from .tower import VisionConfig, VisionTower
 
 _ORIGINALS = {}
 _REUSE = 0   # install(reuse_embeddings=n): keep the last n tower outputs per module (see VisionTower.forward)
+_PRECISION = None   # install(precision=...): operand precision of the towers built from now on (None: $VR2_PRECISION / bf16)
 
 
 def _tower_of(module) -> VisionTower:
@@ -34,7 +35,7 @@ def _tower_of(module) -> VisionTower:
     dev = next(module.parameters()).device
     if tw is None or tw.device != dev:
         cfg = VisionConfig.from_hf(module.config)
-        tw = VisionTower(cfg, module.state_dict(), device=dev)
+        tw = VisionTower(cfg, module.state_dict(), device=dev, precision=_PRECISION)
         module.__dict__["_vr2_tower"] = tw
     return tw
 
@@ -81,14 +82,19 @@ def _rope_5x(self, input_ids=None, mm_token_type_ids=None, image_grid_thw=None, 
                           config=_rope_cfg(self))
 
 
-def install(visual: bool = True, rope_index: bool = True, reuse_embeddings: int = 0):
+def install(visual: bool = True, rope_index: bool = True, reuse_embeddings: int = 0, precision: str = None):
     """Patch the Hugging Face classes in place.  Idempotent.  reuse_embeddings=n keeps the last n tower outputs and
     returns them when the same (unmodified) pixel tensor object is encoded again — GRPO encodes each clip three times
-    per step with a frozen tower; off by default because the returned tensor is then shared between calls."""
+    per step with a frozen tower; off by default because the returned tensor is then shared between calls.
+    precision: "bf16" | "f16" | "split" for the towers built after this call (include/vr2.h vr2_precision; default
+    $VR2_PRECISION, else bf16)."""
     from transformers.models.qwen2_5_vl import modeling_qwen2_5_vl as M
-    from . import lib
-    global _REUSE
+    from . import _lib, lib
+    global _REUSE, _PRECISION
+    if precision is not None and precision not in _lib.PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}, got {precision!r}")
     _REUSE = int(reuse_embeddings)
+    _PRECISION = precision
     lib()  # fail now, loudly, if libvr2.so is missing
     if visual and "visual" not in _ORIGINALS:
         cls = M.Qwen2_5_VisionTransformerPretrainedModel
