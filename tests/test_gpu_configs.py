@@ -104,10 +104,11 @@ def test_config4_long_video_nonsquare(full_tower):
     assert np.array_equal(ex["cu_seqlens"].cpu().numpy(), cu_s)
 
 
-def test_config5_ragged_batch(full_tower):
+@pytest.mark.parametrize("prec", ["bf16", "f16"])
+def test_config5_ragged_batch(full_tower, prec):
     """16 clips of mixed length and resolution in one call (~0.34 M patches)."""
     _, _, towers = full_tower
-    tower = towers["bf16"]
+    tower = towers[prec]
     grid = [_grid(*c) for c in RAGGED]
     sizes = [t * h * w for t, h, w in grid]
     x = _pixels(sum(sizes), 51)
@@ -118,12 +119,13 @@ def test_config5_ragged_batch(full_tower):
     off = np.concatenate([[0], np.cumsum(sizes)])
     for c in (0, 4, 12, 14, 15):                             # incl. the odd merged grid 13 x 23 and the 2-frame clip
         alone = tower(x[off[c]:off[c + 1]], [grid[c]], out_dtype=torch.float32)
-        err, cos = _close(full[off[c] // 4:off[c + 1] // 4], alone, 8e-2)
-        print(f"\nconfig5 clip {c} {RAGGED[c]}: max-abs {err:.2e} cos {cos:.7f}")
-    ex = tower.plan(grid).export()
-    win, cu_w, _ = oidx.window_index(grid)
-    cu_s = oidx.cu_seqlens(grid)
-    assert np.array_equal(ex["window_index"].cpu().numpy(), win)
-    assert np.array_equal(ex["reverse_index"].cpu().numpy(), np.argsort(win, kind="stable"))
-    assert np.array_equal(ex["cu_window_seqlens"].cpu().numpy(), cu_w)
-    assert np.array_equal(ex["cu_seqlens"].cpu().numpy(), cu_s)
+        err, cos = _close(full[off[c] // 4:off[c + 1] // 4], alone, 8e-2 if prec == "bf16" else 1.2e-2)
+        print(f"\nconfig5 [{prec}] clip {c} {RAGGED[c]}: max-abs {err:.2e} cos {cos:.7f}")
+    if prec == "bf16":
+        ex = tower.plan(grid).export()
+        win, cu_w, _ = oidx.window_index(grid)
+        cu_s = oidx.cu_seqlens(grid)
+        assert np.array_equal(ex["window_index"].cpu().numpy(), win)
+        assert np.array_equal(ex["reverse_index"].cpu().numpy(), np.argsort(win, kind="stable"))
+        assert np.array_equal(ex["cu_window_seqlens"].cpu().numpy(), cu_w)
+        assert np.array_equal(ex["cu_seqlens"].cpu().numpy(), cu_s)
