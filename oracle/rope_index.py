@@ -3,24 +3,28 @@
 transformers==4.51.1, the version Video-R2 pins (requirements.txt:3) and calls at
 train/src/train/monkey_patch_forward.py:415-421 / :583-589.
 
-PARITY UNPINNED BY THE REFERENCE: Video-R2 ships no test or golden vector for this
-function, transformers 4.51.1 is not installed here (the installed 5.5.0 has a
-different signature AND different arithmetic), and there is no
-network.  The restatement therefore follows the published 4.51.1 algorithm as
-recorded in SURVEY §8c and is pinned by:
-  * the worked example in the HF docstring (temporal ids 0/50/100, text resumes at 101),
-  * hand-derived known-answer vectors (tests/test_oracle_rope_index.py),
-  * the fp32 truncation vectors measured with torch in SURVEY §8c,
-  * an independent second implementation: vLLM's `get_mrope_input_positions`
-    algorithm re-derived in `vllm_style()` below (float64 there, so compared only
-    where fp32 and fp64 agree).
+PINNING.  Video-R2 ships no test or golden vector for this function and transformers 4.51.1 itself is not
+installed here (no network), so the restatement is pinned against the two LIVE implementations of the same scheme
+that are in the image, through fixtures written by tests/golden/make_golden.py (`rope` section):
+  * tests/golden/rope_vllm.json — the installed vLLM 0.22 `get_mrope_input_positions` (called unbound on a stub
+    `self`), 23 rows incl. the BASELINE config-2 sequence: equal element for element in the multiply-then-truncate
+    mode wherever the fp32 product chain (torch: int64 * float32) and vLLM's float64 product truncate alike — every
+    element for seconds-per-grid values that are exact in binary;
+  * tests/golden/rope_hf55.json — the installed transformers 5.5.0 `get_rope_index` on rows whose vision items have
+    t == 1, where its arithmetic still coincides with 4.51.1 (for t > 1 it diverges: SURVEY §8c); unmasked positions
+    equal, padding (0 there, 1 in 4.51.1) and the delta's length convention are the documented differences;
+plus the worked example of the HF docstring, hand-derived known answers and the fp32 truncation vectors of
+SURVEY §8c (tests/test_oracle_rope_index.py).
 
-Open item: whether 4.51.1 already contained
-`second_per_grid_t = torch.as_tensor(second_per_grid_t, dtype=range_tensor.dtype, ...)`
-which truncates seconds-per-grid to int64 BEFORE the multiply.  The installed
-5.5.0 still truncates (`tokens_per_second * int(next(second_per_grid_ts))`,
-modeling_qwen2_5_vl.py:1110), which is that lineage.  Both behaviours are
-implemented, selected by `spg_int_cast`.
+What no fixture can settle is whether 4.51.1 already contained
+`second_per_grid_t = torch.as_tensor(second_per_grid_t, dtype=range_tensor.dtype, device=range_tensor.device)`,
+which truncates seconds-per-grid to int64 BEFORE the multiply.  Both behaviours are implemented (`spg_int_cast`),
+each bit-exact on the GPU.  The default is the cast, on this evidence: (1) the reference's GRPO / eval callers hand
+`second_per_grid_ts` over as a CUDA tensor (grpo_trainer.py:769 `_prepare_inputs`, lmms_eval/models/qwen2_5_vl.py:
+302-305 `inputs.to(device)`) while `range_tensor = torch.arange(llm_grid_t)` lives on the CPU — without that
+normalising line `cpu_tensor * cuda_0dim_tensor` raises a device-mismatch error, so the version the reference runs
+must contain it; (2) the installed 5.5.0 keeps exactly that truncation (`tokens_per_second * int(next(...))`,
+modeling_qwen2_5_vl.py:1110).  vLLM follows the original float multiply, which is the other mode.
 
 Written with torch tensor ops on purpose: the temporal index depends on torch's
 type promotion (int64 tensor * float32 scalar -> float32), which numpy would not

@@ -198,8 +198,125 @@ def resize_goldens():
     print("helpers", len(sizes), len(frames))
 
 
+def rope_goldens():
+    """Pins for oracle/rope_index.py (the transformers-4.51.1 get_rope_index restatement) from the two live
+    implementations that exist in this image (4.51.1 itself is not installed and there is no network):
+
+      rope_vllm.json   every multimodal row of tests/rope_cases.py::case_suite (unpadded) + extra exactly-representable
+                       second_per_grid_ts cases through the INSTALLED vLLM 0.22 `Qwen2_5_VLForConditionalGeneration.
+                       get_mrope_input_positions` (+ its `iter_mm_grid_thw`), called unbound on a stub `self` that
+                       carries only `config.vision_config`.  vLLM multiplies in float64: it pins the
+                       multiply-then-truncate mode wherever fp32 and fp64 truncation agree (always for spg values
+                       that are exact in binary: 0.5, 1, 2, 2.5, 9.375, ...).
+      rope_hf55.json   rows whose vision items all have t == 1 through the INSTALLED transformers 5.5.0
+                       `Qwen2_5_VLModel.get_rope_index` (stub self, tokens_per_second = 1).  5.5.0 diverges from 4.51.1
+                       for t > 1 (constant temporal index, different h order: SURVEY §8c), zero-fills padding and uses
+                       the unpadded length in the delta; for t == 1 items, unmasked positions and
+                       `delta + (S - unpadded length)` coincide with 4.51.1 and are what the tests compare.
+    """
+    import json
+    import types
+    sys.path.insert(0, os.path.join(HERE, ".."))
+    from rope_cases import IMG, VID, VS, build_row, case_suite, pad_batch
+    from vllm.model_executor.models.qwen2_5_vl import Qwen2_5_VLForConditionalGeneration as VL
+    NS = types.SimpleNamespace
+
+    def vllm_row(tokens, img, vid, spg, tps):
+        stub = NS(config=NS(vision_config=NS(spatial_merge_size=2, tokens_per_second=tps)))
+        stub.iter_mm_grid_thw = types.MethodType(VL.iter_mm_grid_thw, stub)
+        feats, ii, vi = [], 0, 0
+        for j, tok in enumerate(tokens[:-1]):
+            if tok != VS:
+                continue
+            if tokens[j + 1] == IMG:
+                feats.append(NS(mm_position=NS(offset=j + 1), modality="image",
+                                data={"image_grid_thw": NS(data=torch.tensor(img[ii]))}))
+                ii += 1
+            elif tokens[j + 1] == VID:
+                d = {"video_grid_thw": NS(data=torch.tensor(vid[vi]))}
+                if spg is not None:
+                    d["second_per_grid_ts"] = NS(data=torch.tensor(spg[vi], dtype=torch.float32))
+                feats.append(NS(mm_position=NS(offset=j + 1), modality="video", data=d))
+                vi += 1
+        pos, delta = VL.get_mrope_input_positions(stub, list(tokens), feats)
+        return pos.tolist(), int(delta)
+
+    rows = []
+
+    def add_rows(name, kw, tps=2):
+        ids, mask = kw["input_ids"], kw.get("attention_mask")
+        spg = kw.get("second_per_grid_ts")
+        spg32 = None if spg is None else torch.as_tensor(spg, dtype=torch.float32)
+        ii = vi = 0
+        for b in range(ids.shape[0]):
+            toks = (ids[b][mask[b].bool()] if mask is not None else ids[b]).tolist()
+            n_i = sum(1 for j, v in enumerate(toks[:-1]) if v == VS and toks[j + 1] == IMG)
+            n_v = sum(1 for j, v in enumerate(toks[:-1]) if v == VS and toks[j + 1] == VID)
+            if n_i + n_v == 0:
+                continue
+            img = kw["image_grid_thw"][ii:ii + n_i].tolist() if n_i else []
+            vid = kw["video_grid_thw"][vi:vi + n_v].tolist() if n_v else []
+            s = None if spg32 is None or not n_v else [float(spg32[vi + k]) for k in range(n_v)]
+            ii, vi = ii + n_i, vi + n_v
+            pos, delta = vllm_row(toks, img, vid, s, tps)
+            rows.append({"name": f"{name}[{b}]", "tokens": toks, "image_grid_thw": img, "video_grid_thw": vid,
+                         "second_per_grid_ts": s, "tokens_per_second": tps, "pos": pos, "delta": delta})
+
+    for name, kw in case_suite():
+        if "image_grid_thw" in kw or "video_grid_thw" in kw:
+            add_rows(name, kw)
+    rng = np.random.default_rng(7)
+    # exactly representable seconds-per-grid (fp32 == fp64 for every k): the whole temporal row is pinned
+    for spg in (0.5, 0.25, 1.5, 2.5, 9.375, 4.0, 0.125):
+        g = [int(rng.integers(2, 14)), 4, 6]
+        add_rows(f"exact_spg_{spg}", dict(input_ids=torch.tensor([build_row([(VID, g)], rng)]),
+                                          video_grid_thw=torch.tensor([g]), second_per_grid_ts=torch.tensor([spg])))
+    # the HF docstring shape: tokens_per_second 25, 2 s per grid
+    add_rows("docstring_tps25", dict(input_ids=torch.tensor([[VS] + [VID] * 12 + [11, 12, 13, 14, 15]]),
+                                     video_grid_thw=torch.tensor([[3, 4, 4]]), second_per_grid_ts=torch.tensor([2.0])), tps=25)
+    # BASELINE config 2 sequence (32 frames 448x448), fps 2 -> 1 s per grid
+    g = [16, 32, 32]
+    add_rows("config2", dict(input_ids=torch.tensor([build_row([(VID, g)], rng, lead=32, gap=0, tail=64)]),
+                             video_grid_thw=torch.tensor([g]), second_per_grid_ts=torch.tensor([1.0])))
+    with open(os.path.join(HERE, "rope_vllm.json"), "w") as f:
+        json.dump({"source": "vllm 0.22 Qwen2_5_VLForConditionalGeneration.get_mrope_input_positions (float64 temporal index)",
+                   "rows": rows}, f, separators=(",", ":"))
+    print("rope vllm rows", len(rows))
+
+    # ---- transformers 5.5.0, t == 1 items only
+    from transformers.models.qwen2_5_vl import modeling_qwen2_5_vl as M
+    hf_stub = NS(config=NS(vision_config=NS(spatial_merge_size=2, tokens_per_second=1)))
+    hf_stub.get_vision_position_ids = types.MethodType(M.Qwen2_5_VLModel.get_vision_position_ids, hf_stub)
+    batches = []
+    im1, im2, im3, v1 = [1, 6, 4], [1, 2, 2], [1, 10, 8], [1, 4, 12]
+    specs = {
+        "images_right": ([[(IMG, im1), (IMG, im2)], [(IMG, im3)], []], "right"),
+        "images_left": ([[(IMG, im1), (IMG, im2)], [(IMG, im3)], []], "left"),
+        "t1_video_and_image": ([[(VID, v1), (IMG, im2)], [(IMG, im1), (VID, v1)]], "left"),
+    }
+    for name, (spec, side) in specs.items():
+        rws = [build_row(items, rng) if items else rng.integers(1000, 5000, size=9).tolist() for items in spec]
+        ids, mask = pad_batch(rws, side)
+        img = [g for items in spec for k, g in items if k == IMG]
+        vid = [g for items in spec for k, g in items if k == VID]
+        types_ = torch.zeros_like(ids)
+        types_[ids == IMG] = 1
+        types_[ids == VID] = 2
+        pos, delta = M.Qwen2_5_VLModel.get_rope_index(
+            hf_stub, ids, types_, torch.tensor(img) if img else None, torch.tensor(vid) if vid else None, None, mask)
+        batches.append({"name": name, "input_ids": ids.tolist(), "attention_mask": mask.tolist(), "image_grid_thw": img,
+                        "video_grid_thw": vid, "tokens_per_second": 1, "pos": pos.tolist(), "delta": delta.flatten().tolist()})
+    import transformers
+    with open(os.path.join(HERE, "rope_hf55.json"), "w") as f:
+        json.dump({"source": f"transformers {transformers.__version__} Qwen2_5_VLModel.get_rope_index, t == 1 items, tokens_per_second 1",
+                   "batches": batches}, f, separators=(",", ":"))
+    print("rope hf55 batches", len(batches))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["tower", "patchify", "mrope", "resize"]
+    which = sys.argv[1:] or ["tower", "patchify", "mrope", "resize", "rope"]
+    if "rope" in which:
+        rope_goldens()
     if "tower" in which:
         main()
     if "patchify" in which:

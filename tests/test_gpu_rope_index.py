@@ -65,3 +65,49 @@ def test_config2_sequence_and_long_batch(int_cast):
                   second_per_grid_ts=torch.tensor([2 / f for f in (2.0, 1.0, 0.2133, 0.7, 3.0, 1.7)]))
         pos, delta, rpos, rdelta = _run_both(kw, int_cast)
         assert torch.equal(pos, rpos) and torch.equal(delta, rdelta)
+
+
+# ---- the CUDA kernel against the fixtures of the two live implementations directly (no oracle in between)
+import json
+import os
+
+_G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+with open(os.path.join(_G, "rope_vllm.json")) as _f:
+    _VLLM = [r for r in json.load(_f)["rows"]
+             if r["name"].startswith(("exact_spg", "config2", "docstring", "video_nomask", "image_only", "video_spg_none",
+                                      "video_list_spg"))]
+with open(os.path.join(_G, "rope_hf55.json")) as _f:
+    _HF55 = json.load(_f)["batches"]
+
+
+@pytest.mark.parametrize("row", _VLLM, ids=[r["name"] for r in _VLLM])
+def test_kernel_vs_installed_vllm_fixture(row):
+    """Rows whose seconds-per-grid values are exact in binary: fp32 == fp64, so vLLM's output is the expected output of
+    the multiply-then-truncate mode, element for element."""
+    import video_r2_b200 as vr2
+    ids = torch.tensor([row["tokens"]]).cuda()
+    img = torch.tensor(row["image_grid_thw"]).cuda() if row["image_grid_thw"] else None
+    vid = torch.tensor(row["video_grid_thw"]).cuda() if row["video_grid_thw"] else None
+    spg = None if row["second_per_grid_ts"] is None else torch.tensor(row["second_per_grid_ts"], dtype=torch.float32).cuda()
+    cfg = vr2.RopeConfig(spg_int_cast=False, tokens_per_second=row["tokens_per_second"])
+    pos, delta = vr2.get_rope_index(ids, img, vid, spg, None, config=cfg)
+    ref = torch.tensor(row["pos"])
+    assert torch.equal(pos[:, 0].cpu(), ref), row["name"]
+    assert int(delta.cpu()) == row["delta"]
+
+
+@pytest.mark.parametrize("b", _HF55, ids=[b["name"] for b in _HF55])
+def test_kernel_vs_installed_transformers_fixture(b):
+    import video_r2_b200 as vr2
+    ids, mask = torch.tensor(b["input_ids"]), torch.tensor(b["attention_mask"])
+    img = torch.tensor(b["image_grid_thw"]).cuda() if b["image_grid_thw"] else None
+    vid = torch.tensor(b["video_grid_thw"]).cuda() if b["video_grid_thw"] else None
+    for int_cast in (True, False):
+        cfg = vr2.RopeConfig(spg_int_cast=int_cast, tokens_per_second=b["tokens_per_second"])
+        pos, delta = vr2.get_rope_index(ids.cuda(), img, vid, None, mask.cuda(), config=cfg)
+        pos, delta = pos.cpu(), delta.cpu()
+        ref = torch.tensor(b["pos"])
+        m = mask.bool()
+        assert torch.equal(pos[:, m], ref[:, m])
+        assert (pos[:, ~m] == 1).all()
+        assert torch.equal(delta.flatten() + (mask.shape[1] - mask.sum(1)), torch.tensor(b["delta"]))

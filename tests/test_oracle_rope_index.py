@@ -83,3 +83,97 @@ def test_against_independent_second_implementation(name, kw):
         # fp32-vs-fp64 disagreement only ever moves a temporal index by 1; h/w rows and text must match exactly
         assert np.array_equal(got[1:].numpy(), ref[1:])
         assert np.abs(got[0].numpy() - ref[0]).max() <= 1
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Pins from the two LIVE implementations in the image (fixtures written by tests/golden/make_golden.py rope):
+# the installed vLLM's get_mrope_input_positions and the installed transformers-5.5.0 get_rope_index.
+# ---------------------------------------------------------------------------------------------------------------
+import json
+import os
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _load(name):
+    with open(os.path.join(GOLDEN, name)) as f:
+        return json.load(f)
+
+
+def _agreeing_temporal_mask(row):
+    """Per token: True where the fp32 product chain of 4.51.1 (torch: int64 * float32 -> float32) and vLLM's float64
+    product truncate to the same integer — computed here with numpy, independently of the oracle."""
+    toks = np.asarray(row["tokens"])
+    ok = np.ones(len(toks), dtype=bool)
+    spg = row["second_per_grid_ts"]
+    if not row["video_grid_thw"]:
+        return ok, 0
+    tps = row["tokens_per_second"]
+    pads = np.flatnonzero(toks == VID)
+    at = 0
+    disagree = 0
+    for vi, (t, h, w) in enumerate(row["video_grid_thw"]):
+        per = (h // 2) * (w // 2)
+        s = 1.0 if spg is None else spg[vi]
+        k = np.arange(t)
+        f32 = np.trunc((k.astype(np.float32) * np.float32(s)).astype(np.float32) * np.float32(tps)).astype(np.int64)
+        f64 = (k * float(s) * tps).astype(np.int64)
+        same = np.repeat(f32 == f64, per)
+        ok[pads[at:at + t * per]] = same
+        disagree += int((~same).sum())
+        at += t * per
+    # a disagreement in a video's LAST slice can shift everything behind it (text resumes at max + 1)
+    if disagree:
+        first_bad = int(np.flatnonzero(~ok)[0])
+        ok[first_bad:] = False
+    return ok, disagree
+
+
+VLLM_ROWS = _load("rope_vllm.json")["rows"]
+
+
+@pytest.mark.parametrize("row", VLLM_ROWS, ids=[r["name"] for r in VLLM_ROWS])
+def test_pinned_by_installed_vllm(row):
+    """multiply-then-truncate mode == vLLM 0.22's real get_mrope_input_positions, element for element, wherever the fp32
+    and fp64 products truncate alike (every element for exactly representable seconds-per-grid values)."""
+    ids = torch.tensor([row["tokens"]])
+    img = torch.tensor(row["image_grid_thw"]) if row["image_grid_thw"] else None
+    vid = torch.tensor(row["video_grid_thw"]) if row["video_grid_thw"] else None
+    spg = None if row["second_per_grid_ts"] is None else torch.tensor(row["second_per_grid_ts"], dtype=torch.float32)
+    pos, delta = R.get_rope_index(ids, img, vid, spg, None, tokens_per_second=row["tokens_per_second"], spg_int_cast=False)
+    ref = np.asarray(row["pos"])
+    ok, disagree = _agreeing_temporal_mask(row)
+    got = pos[:, 0].numpy()
+    assert np.array_equal(got[:, ok], ref[:, ok]), row["name"]
+    assert np.abs(got - ref).max() <= 1          # a truncation disagreement moves an index by at most one
+    if disagree == 0:
+        assert int(delta) == row["delta"]
+    if row["name"].startswith(("exact_spg", "config2", "docstring", "video_nomask", "image_only", "video_spg_none")):
+        assert disagree == 0 and ok.all()        # these rows are pinned completely
+
+
+def test_vllm_fixture_covers_every_branch():
+    names = " ".join(r["name"] for r in VLLM_ROWS)
+    for need in ("mixed_batch_leftpad", "grpo_repeat", "image_only", "video_frac_spg", "exact_spg_9.375", "config2"):
+        assert need in names
+    assert sum(len(r["tokens"]) for r in VLLM_ROWS) > 5000
+
+
+HF55 = _load("rope_hf55.json")["batches"]
+
+
+@pytest.mark.parametrize("b", HF55, ids=[b["name"] for b in HF55])
+def test_pinned_by_installed_transformers_on_t1_items(b):
+    """transformers 5.5.0's live get_rope_index on rows whose vision items all have t == 1 (where its arithmetic still
+    coincides with 4.51.1): unmasked positions equal; its delta uses the unpadded length, 4.51.1 the padded one."""
+    ids, mask = torch.tensor(b["input_ids"]), torch.tensor(b["attention_mask"])
+    img = torch.tensor(b["image_grid_thw"]) if b["image_grid_thw"] else None
+    vid = torch.tensor(b["video_grid_thw"]) if b["video_grid_thw"] else None
+    for int_cast in (True, False):
+        pos, delta = R.get_rope_index(ids, img, vid, None, mask, tokens_per_second=b["tokens_per_second"], spg_int_cast=int_cast)
+        ref = torch.tensor(b["pos"])
+        m = mask.bool()
+        assert torch.equal(pos[:, m], ref[:, m])
+        assert (pos[:, ~m] == 1).all() and (ref[:, ~m] == 0).all()       # the documented padding difference
+        pad = mask.shape[1] - mask.sum(1)
+        assert torch.equal(delta.flatten() + pad, torch.tensor(b["delta"]))
