@@ -130,12 +130,22 @@ int vr2_tower_create(const vr2_tower_config* cfg, int32_t cuda_device, vr2_tower
  *                        the GEMMs read fp16 copies of the bf16 weights (exact inside fp16's normal range; +1.35 GB,
  *                        made on first use), the patch embedding still multiplies bf16 pixels by bf16 weights.  The
  *                        work and the speed are those of VR2_PRECISION_BF16 with ~8x less operand rounding: also
- *                        meets 2e-2.  Conversions saturate at +-65504 (fp16's range); a checkpoint whose
- *                        activations exceed that needs BF16 or SPLIT.
+ *                        meets 2e-2.  Conversions saturate at +-65504 (fp16's range) and every epilogue that
+ *                        converts COUNTS the values it clamped (NaN included) in a device counter:
+ *                        vr2_tower_saturation_count.  A forward whose count is non-zero must be repeated in SPLIT
+ *                        (the Python host's default "auto" precision does exactly that).
  * Changes vr2_tower_workspace_bytes(); call before sizing the workspace. */
 typedef enum vr2_precision { VR2_PRECISION_BF16 = 0, VR2_PRECISION_SPLIT = 1, VR2_PRECISION_F16 = 2 } vr2_precision;
 int vr2_tower_set_precision(vr2_tower* tower, int32_t precision);
 int32_t vr2_tower_get_precision(const vr2_tower* tower);
+/* Range guard of VR2_PRECISION_F16: *count_host = number of (thread, tile) conversions since the last reset that met a
+ * value outside fp16's finite range, over every forward enqueued on `stream` so far (the call synchronises `stream`).
+ * 0 means no activation was clamped: the result is what unbounded-range fp16 arithmetic would give.  reset != 0
+ * zeroes the counter (stream-ordered).  Always 0 in the other precisions. */
+int vr2_tower_saturation_count(vr2_tower* tower, uint64_t* count_host, int32_t reset, void* stream);
+/* The same counter copied, stream-ordered and without synchronising, to a 4-byte destination in pinned host or device
+ * memory: a pipelined caller snapshots it behind every forward and compares neighbours once the batch is complete. */
+int vr2_tower_saturation_snapshot(vr2_tower* tower, uint32_t* dst, void* stream);
 void vr2_tower_destroy(vr2_tower* tower);
 /* One call per entry of the HF module's state_dict (names relative to the
  * vision module: "patch_embed.proj.weight", "blocks.0.norm1.weight",
@@ -205,14 +215,20 @@ typedef struct vr2_rope_config {
 /* input_ids_dev [B,S] int64; mask_dev [B,S] of mask_dtype (I64/I32/U8) or NULL;
  * image_thw_dev [n_img,3] / video_thw_dev [n_vid,3] int64 or NULL;
  * second_per_grid_ts_dev [n_vid] fp32 or NULL;
- * scratch_dev: B*S int32 + 2*B int32 (vr2_rope_scratch_bytes);
+ * scratch_dev: vr2_rope_scratch_bytes(B, S) bytes;
  * position_ids_dev [3,B,S] int64; deltas_dev [B] int64.
- * With both grids NULL this is the text-only branch. */
+ * With both grids NULL this is the text-only branch.
+ * A row that names more images / videos than the grids describe (or names one while that grid pointer is NULL)
+ * makes Hugging Face raise; the kernel never reads through a NULL or past-the-end grid pointer: the item is not
+ * placed, the rest of the row is numbered as text and a status word is set in the scratch buffer.
+ * vr2_rope_index_status copies it to the host (synchronises `stream`): 0 = every item placed, bit 0 = image grid
+ * missing / too short, bit 1 = video grid missing / too short. */
 size_t vr2_rope_scratch_bytes(int32_t B, int32_t S);
 int vr2_rope_index(const vr2_rope_config* cfg, const int64_t* input_ids_dev, const void* mask_dev, int32_t mask_dtype,
                    int32_t B, int32_t S, const int64_t* image_thw_dev, int32_t n_img, const int64_t* video_thw_dev,
                    int32_t n_vid, const float* second_per_grid_ts_dev, void* scratch_dev, int64_t* position_ids_dev,
                    int64_t* deltas_dev, void* stream);
+int vr2_rope_index_status(const void* scratch_dev, int32_t B, int32_t S, int32_t* status_host, void* stream);
 
 /* ------------------------------------------------------------------------
  * Placing visual tokens for the decoder (monkey_patch_forward.py:372-406).

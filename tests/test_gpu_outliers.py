@@ -1,0 +1,123 @@
+"""GPU: the f16 activation mode on activations it was not tuned on (VERDICT r1 "what's weak": every other test runs on
+N(0, 0.02) random init, while real Qwen2.5-VL towers carry massive residual channels — SURVEY §9 V5).
+
+Outliers are injected into the weights so that (a) the fp32 residual stream carries channels thousands of times the
+typical magnitude but every 16-bit operand still fits fp16, (b) the residual-stream operand `x * w_norm` leaves fp16's
+range, (c) the SwiGLU product `silu(g) * u` leaves it.  Asserted, against the fp32 oracle:
+  * in range  -> the guard stays at 0 and f16 meets the (scale-relative) north-star tolerance;
+  * out of range -> the guard counts, precision "auto" repeats the call with hi+lo bf16 operands (bit-identical to
+    "split") and that result meets the tolerance;  plain "f16" without the guard would have been silently wrong.
+"""
+import pytest
+import torch
+
+from oracle import tower as T
+
+pytestmark = pytest.mark.gpu
+
+GRID = [[2, 8, 12], [1, 4, 6]]
+N = sum(t * h * w for t, h, w in GRID)
+
+
+def _stats(out, ref):
+    out, ref = out.float().cpu(), ref.float().cpu()
+    scale = max(1.0, ref.abs().max().item() / 7.2)       # 7.2 = |max| of the random-init output the 2e-2 bound is quoted on
+    err = (out - ref).abs().max().item() / scale
+    cos = torch.nn.functional.cosine_similarity(out.flatten(), ref.flatten(), dim=0).item()
+    return err, cos
+
+
+def _case(kind):
+    cfg = T.TowerConfig(depth=4, fullatt_block_indexes=(1, 3))
+    w = T.make_weights(cfg, seed=41)
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(N, 1176, generator=g).to(torch.bfloat16)
+    if kind == "massive_in_range":
+        # three residual channels ~3e3 (typical entries are ~1): the down projection of block 0 feeds them
+        for c, k in ((7, 1.2e4), (300, -8e3), (1111, 6e3)):
+            w["blocks.0.mlp.down_proj.weight"][c] *= k
+        x[:, 5] *= 50.0                                     # and a hot pixel column
+    elif kind == "residual_out_of_range":
+        for c, k in ((7, 8e5), (300, -5e5)):               # |x| ~ 2e5 > 65504
+            w["blocks.0.mlp.down_proj.weight"][c] *= k
+    elif kind == "swiglu_out_of_range":
+        for r in (3, 1500, 3419):                           # silu(g) * u ~ (0.7 * 600)^2 > 65504
+            w["blocks.1.mlp.gate_proj.weight"][r] *= 600.0
+            w["blocks.1.mlp.up_proj.weight"][r] *= 600.0
+    else:
+        raise KeyError(kind)
+    w = {k: v.to(torch.bfloat16).float() for k, v in w.items()}
+    ref, hidden = T.tower_forward(w, cfg, x.float(), GRID, return_hidden=True)
+    return cfg, w, x, ref, hidden
+
+
+def _tower(cfg_o, weights, precision):
+    import video_r2_b200 as vr2
+    cfg = vr2.VisionConfig(depth=cfg_o.depth, fullatt_block_indexes=tuple(cfg_o.fullatt_block_indexes))
+    return vr2.VisionTower(cfg, weights, device="cuda:0", precision=precision)
+
+
+def test_massive_but_in_range_activations_keep_f16_exact_enough():
+    cfg, w, x, ref, hidden = _case("massive_in_range")
+    assert hidden.abs().max() > 1e3                          # the stream really carries massive channels
+    tw = _tower(cfg, w, "f16")
+    out = tw(x.cuda(), GRID, out_dtype=torch.float32)
+    assert tw.saturation_count() == 0
+    e, c = _stats(out, ref)
+    print(f"\nmassive in-range: |hidden|max {hidden.abs().max():.0f}  f16 max-abs/scale {e:.5f} cos {c:.7f}")
+    assert e <= 2e-2 and c >= 0.9995, (e, c)
+    auto = _tower(cfg, w, "auto")
+    assert torch.equal(auto(x.cuda(), GRID, out_dtype=torch.float32), out) and auto.fallbacks == 0
+
+
+@pytest.mark.parametrize("kind", ["residual_out_of_range", "swiglu_out_of_range"])
+def test_out_of_range_activations_trip_the_guard_and_auto_falls_back(kind):
+    cfg, w, x, ref, hidden = _case(kind)
+    f16 = _tower(cfg, w, "f16")
+    out_h = f16(x.cuda(), GRID, out_dtype=torch.float32)
+    tripped = f16.saturation_count()
+    assert tripped > 0, "values beyond 65504 were converted without being counted"
+    assert f16.saturation_count() == 0                       # the read resets the counter
+    split = _tower(cfg, w, "split")
+    out_s = split(x.cuda(), GRID, out_dtype=torch.float32)
+    with pytest.warns(UserWarning, match="saturation guard"):
+        auto = _tower(cfg, w, "auto")
+        out_a = auto(x.cuda(), GRID, out_dtype=torch.float32)
+    assert auto.fallbacks == 1 and torch.equal(out_a, out_s)
+    e_s, c_s = _stats(out_s, ref)
+    e_h, c_h = _stats(out_h, ref)
+    print(f"\n{kind}: guard {tripped}  split max-abs/scale {e_s:.5f} cos {c_s:.7f} | unguarded f16 {e_h:.4f} cos {c_h:.6f}")
+    assert e_s <= 2e-2 and c_s >= 0.9995, (e_s, c_s)
+    # a second call on in-range data with the same tower: no fallback, f16 speed path
+    x2 = torch.randn(N, 1176, generator=torch.Generator().manual_seed(5)).to(torch.bfloat16)
+    auto.forward_into(x2.cuda(), GRID, torch.zeros(N // 4, 3584, device="cuda"), torch.arange(N // 4, device="cuda"))
+
+
+def test_guard_is_silent_on_the_golden_shapes():
+    """The random-init goldens never clamp: count 0 (so "auto" == "f16" bit for bit there)."""
+    cfg = T.TowerConfig(depth=4, fullatt_block_indexes=(1, 3))
+    w = T.make_weights(cfg, seed=21)
+    x = torch.randn(N, 1176, generator=torch.Generator().manual_seed(22)).to(torch.bfloat16).cuda()
+    a, h = _tower(cfg, w, "auto"), _tower(cfg, w, "f16")
+    assert torch.equal(a(x, GRID), h(x, GRID)) and a.fallbacks == 0 and h.saturation_count() == 0
+
+
+def test_pipeline_repeats_a_clamped_batch():
+    """HostPipeline snapshots the guard behind every batch and recomputes only the batch that clamped."""
+    import video_r2_b200 as vr2
+    cfg, w, x_bad, ref, _ = _case("swiglu_out_of_range")
+    tw = _tower(cfg, w, "auto")
+    # an input that stays in range with the same weights: zero pixels (biases only)
+    x_ok = torch.zeros_like(x_bad)
+    split = _tower(cfg, w, "split")
+    want_bad = split(x_bad.cuda(), GRID).cpu()
+    f16 = _tower(cfg, w, "f16")
+    want_ok = f16(x_ok.cuda(), GRID).cpu()
+    if f16.saturation_count() != 0:
+        pytest.skip("zero pixels also clamp with these weights")
+    pipe = vr2.HostPipeline(tw, depth=2)
+    for xh in (x_ok, x_bad, x_ok):
+        pipe.submit(xh.pin_memory(), GRID)
+    outs = [o.clone() for o, _ in pipe.results()]
+    assert pipe.fallbacks == 1
+    assert torch.equal(outs[0], want_ok) and torch.equal(outs[2], want_ok) and torch.equal(outs[1], want_bad)

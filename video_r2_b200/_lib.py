@@ -11,6 +11,10 @@ LIB_PATH = os.environ.get("VR2_LIB") or os.path.join(_HERE, "libvr2.so")   # VR2
 VR2_F32, VR2_BF16, VR2_I64, VR2_I32, VR2_U8, VR2_F16 = 0, 1, 2, 3, 4, 5
 VR2_PRECISION_BF16, VR2_PRECISION_SPLIT, VR2_PRECISION_F16 = 0, 1, 2
 PRECISIONS = {"bf16": VR2_PRECISION_BF16, "split": VR2_PRECISION_SPLIT, "f16": VR2_PRECISION_F16}
+# host-side policies on top of the library's three precisions: "auto" = f16 with the saturation guard read after every
+# forward and an automatic re-run in split when anything was clamped (the default: meets max-abs 2e-2 at full speed on
+# in-range activations, and is never silently wrong on outliers)
+HOST_PRECISIONS = dict(PRECISIONS, auto=VR2_PRECISION_F16)
 
 
 class Vr2Error(RuntimeError):
@@ -93,12 +97,15 @@ SIGNATURES = {
                                   C.POINTER(C.c_int32), C.c_float, _P]),
     "vr2_lm_logprob_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "vr2_lm_logprob": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_float, _P, _P, C.c_size_t, _P]),
+    "vr2_tower_saturation_count": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_int32, _P]),
+    "vr2_tower_saturation_snapshot": (C.c_int, [_P, _P, _P]),
     "vr2_tower_profile": (C.c_int, [_P, C.c_uint32]),
     "vr2_tower_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "vr2_tower_launch_count": (C.c_int64, [_P, _P, C.c_int32]),
     "vr2_rope_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "vr2_rope_index": (C.c_int, [C.POINTER(RopeConfig), _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, _P,
                                  C.c_int32, _P, _P, _P, _P, _P]),
+    "vr2_rope_index_status": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(C.c_int32), _P]),
     "vr2_op_linear": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "vr2_op_linear_f16": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "vr2_op_linear_split": (C.c_int, [_P, _P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),

@@ -30,8 +30,9 @@ __global__ void cast_f32_bf16_kernel(const float4* __restrict__ src, uint2* __re
 // one warp per row; dim % 128 == 0 (32 lanes x float4)
 __global__ void rmsnorm_bf16_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                     __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_lo, int64_t rows,
-                                    int dim, float eps, bool f16) {
+                                    int dim, float eps, bool f16, unsigned int* __restrict__ sat) {
   const int lane = threadIdx.x & 31;
+  float amax = 0.f;   // f16 range guard
   const int64_t warp0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 5;
   for (int64_t row = warp0; row < rows; row += nwarps) {
@@ -51,8 +52,10 @@ __global__ void rmsnorm_bf16_kernel(const float* __restrict__ x, const float* __
       const float4 g = __ldg(reinterpret_cast<const float4*>(w) + v);
       uint32_t h0, h1, l0 = 0, l1 = 0;
       if (f16) {                                    // fp16 activations (never with out_lo)
-        h0 = pack_f16x2(a.x * rstd * g.x, a.y * rstd * g.y);
-        h1 = pack_f16x2(a.z * rstd * g.z, a.w * rstd * g.w);
+        const float v0 = a.x * rstd * g.x, v1 = a.y * rstd * g.y, v2 = a.z * rstd * g.z, v3 = a.w * rstd * g.w;
+        h0 = pack_f16x2(v0, v1);
+        h1 = pack_f16x2(v2, v3);
+        amax = fmaxf(fmaxf(amax, fmaxf(fabsf(v0), fabsf(v1))), fmaxf(fabsf(v2), fabsf(v3)));
       } else {
         split_bf16x2(a.x * rstd * g.x, a.y * rstd * g.y, h0, l0);
         split_bf16x2(a.z * rstd * g.z, a.w * rstd * g.w, h1, l1);
@@ -61,6 +64,7 @@ __global__ void rmsnorm_bf16_kernel(const float* __restrict__ x, const float* __
       if (lrow != nullptr) lrow[v] = make_uint2(l0, l1);
     }
   }
+  if (f16 && sat != nullptr) sat_guard(amax, sat);
 }
 
 template <typename Src, typename Dst>
@@ -114,9 +118,9 @@ cudaError_t cast_bf16_to_f16(const __nv_bfloat16* src, void* dst, int64_t n, cud
 }
 
 cudaError_t rmsnorm_to_bf16(const float* x, const float* w, __nv_bfloat16* out, __nv_bfloat16* out_lo, int64_t rows,
-                            int dim, float eps, cudaStream_t stream, bool f16) {
+                            int dim, float eps, cudaStream_t stream, bool f16, unsigned int* sat) {
   if (dim % 4 != 0 || (f16 && out_lo != nullptr)) return cudaErrorInvalidValue;
-  rmsnorm_bf16_kernel<<<grid_for(rows * 32, 256), 256, 0, stream>>>(x, w, out, out_lo, rows, dim, eps, f16);
+  rmsnorm_bf16_kernel<<<grid_for(rows * 32, 256), 256, 0, stream>>>(x, w, out, out_lo, rows, dim, eps, f16, sat);
   return cudaGetLastError();
 }
 

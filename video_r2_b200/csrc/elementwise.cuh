@@ -12,7 +12,7 @@ cudaError_t cast_f32_to_bf16(const float* src, __nv_bfloat16* dst, __nv_bfloat16
 // out = bf16(x * rsqrt(mean(x^2) + eps) * w), one warp per row; out_lo (nullable) = its rounding residual
 cudaError_t cast_bf16_to_f16(const __nv_bfloat16* src, void* dst_f16, int64_t n, cudaStream_t stream);
 cudaError_t rmsnorm_to_bf16(const float* x, const float* w, __nv_bfloat16* out, __nv_bfloat16* out_lo, int64_t rows,
-                            int dim, float eps, cudaStream_t stream, bool f16 = false);
+                            int dim, float eps, cudaStream_t stream, bool f16 = false, unsigned int* sat = nullptr);
 
 // dst[(r / blk) * blk_stride + offset + r % blk][c] = src[r][c]  (dtype converted);
 // dst must be zero-filled beforehand where padding is wanted.

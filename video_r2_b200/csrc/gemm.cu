@@ -123,21 +123,30 @@ __device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + e
 __device__ __forceinline__ float silu(float v) { return __fdividef(v, 1.0f + __expf(-v)); }
 
 // f16: GEMM_OUT_F16 (the f16 activation mode; never together with SPLIT)
+// sat: the f16 mode's saturation counter (null otherwise): bumped when a value outside fp16's finite range is converted
 template <bool SPLIT>
-__device__ __forceinline__ void pack16(const float* f, uint32_t* hi, uint32_t* lo, bool f16) {
+__device__ __forceinline__ void pack16(const float* f, uint32_t* hi, uint32_t* lo, bool f16, unsigned int* sat) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     if constexpr (SPLIT) split_bf16x2(f[2 * j], f[2 * j + 1], hi[j], lo[j]);
     else hi[j] = pack16x2_rt(f[2 * j], f[2 * j + 1], f16);
+  }
+  if constexpr (!SPLIT) {
+    if (sat != nullptr) {
+      float amax = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) amax = fmaxf(amax, fabsf(f[j]));
+      sat_guard(amax, sat);
+    }
   }
 }
 // This thread's row, 16 consecutive columns -> the bf16 piece whose (row0, column) origin is g (and its
 // rounding residual to g_lo), row-contiguous through the warp's staging tile.
 template <bool SPLIT>
 __device__ __forceinline__ void emit_piece(const Stage& st, const float* f, __nv_bfloat16* g, __nv_bfloat16* g_lo,
-                                           int64_t ld, int rows_valid, int lane, int width, bool f16) {
+                                           int64_t ld, int rows_valid, int lane, int width, bool f16, unsigned int* sat) {
   uint32_t hi[8], lo[8];
-  pack16<SPLIT>(f, hi, lo, f16);
+  pack16<SPLIT>(f, hi, lo, f16, sat);
   *st.h8(lane, 0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
   *st.h8(lane, 1) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
   __syncwarp();
@@ -153,9 +162,9 @@ __device__ __forceinline__ void emit_piece(const Stage& st, const float* f, __nv
 }
 // Same piece, thread-per-row (scattered destination rows): o / o_lo point at this row's 16 columns.
 template <bool SPLIT>
-__device__ __forceinline__ void emit_row(const float* f, __nv_bfloat16* o, __nv_bfloat16* o_lo, bool f16) {
+__device__ __forceinline__ void emit_row(const float* f, __nv_bfloat16* o, __nv_bfloat16* o_lo, bool f16, unsigned int* sat) {
   uint32_t hi[8], lo[8];
-  pack16<SPLIT>(f, hi, lo, f16);
+  pack16<SPLIT>(f, hi, lo, f16, sat);
   *reinterpret_cast<uint4*>(o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
   *reinterpret_cast<uint4*>(o + 8) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
   if constexpr (SPLIT) {
@@ -186,6 +195,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const bool of16 = (p.flags & GEMM_OUT_F16) != 0;
+  unsigned int* const osat = of16 ? p.sat : nullptr;   // range guard of the f16 activation mode
   const int num_n_blocks = (p.N + BN - 1) / BN;
   const int num_m_blocks = (p.M + BM - 1) / BM;
   const int num_tiles = num_m_blocks * num_n_blocks;
@@ -345,12 +355,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           } else {
             const int64_t off = n0 + c;
             if (direct) {
-              if (store_row) emit_row<SPLIT>(f, p.out_bf16 + dest * p.ld_out + off, p.out_lo ? p.out_lo + dest * p.ld_out + off : nullptr, of16);
+              if (store_row) emit_row<SPLIT>(f, p.out_bf16 + dest * p.ld_out + off, p.out_lo ? p.out_lo + dest * p.ld_out + off : nullptr, of16, osat);
             } else if (SPLIT && p.out_lo == nullptr) {
-              emit_piece<false>(st, f, p.out_bf16 + static_cast<int64_t>(row0) * p.ld_out + off, nullptr, p.ld_out, rows_valid, lane, 16, of16);
+              emit_piece<false>(st, f, p.out_bf16 + static_cast<int64_t>(row0) * p.ld_out + off, nullptr, p.ld_out, rows_valid, lane, 16, of16, osat);
             } else {
               emit_piece<SPLIT>(st, f, p.out_bf16 + static_cast<int64_t>(row0) * p.ld_out + off,
-                                p.out_lo + static_cast<int64_t>(row0) * p.ld_out + off, p.ld_out, rows_valid, lane, 16, of16);
+                                p.out_lo + static_cast<int64_t>(row0) * p.ld_out + off, p.ld_out, rows_valid, lane, 16, of16, osat);
             }
           }
         }
@@ -419,10 +429,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               for (int j = 0; j < 16; j += 4)
                 if (j < wdt) *reinterpret_cast<float4*>(xr + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
               if (wdt == 16) {
-                emit_row<SPLIT>(xw, p.out_bf16 + dest * p.ld_out + n0 + c, p.out_lo ? p.out_lo + dest * p.ld_out + n0 + c : nullptr, of16);
+                emit_row<SPLIT>(xw, p.out_bf16 + dest * p.ld_out + n0 + c, p.out_lo ? p.out_lo + dest * p.ld_out + n0 + c : nullptr, of16, osat);
               } else {
                 uint32_t hi[8], lo[8];
-                pack16<SPLIT>(xw, hi, lo, of16);
+                pack16<SPLIT>(xw, hi, lo, of16, osat);
                 *reinterpret_cast<uint4*>(p.out_bf16 + dest * p.ld_out + n0 + c) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
                 if constexpr (SPLIT) {
                   if (p.out_lo != nullptr)
@@ -438,7 +448,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             st.store_f32_w(xg, p.ldx, rows_valid, lane, wdt);
             __syncwarp();
             const int64_t off = static_cast<int64_t>(row0) * p.ld_out + n0 + c;
-            emit_piece<SPLIT>(st, xw, p.out_bf16 + off, p.out_lo + off, p.ld_out, rows_valid, lane, wdt, of16);
+            emit_piece<SPLIT>(st, xw, p.out_bf16 + off, p.out_lo + off, p.ld_out, rows_valid, lane, wdt, of16, osat);
           }
         }
         // one partial per (row, column group), part-major [N/40][M]: deterministic, no atomics, coalesced both ways
@@ -523,6 +533,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               bh[q] = pack16x2_rt(b[2 * q], b[2 * q + 1], of16);
             }
           }
+          if (!SPLIT && osat != nullptr) {
+            float amax = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) amax = fmaxf(amax, fmaxf(fabsf(a[q]), fabsf(b[q])));
+            sat_guard(amax, osat);
+          }
           const int half = lane & 1;
           const int64_t piece = og + (half ? 40 + i0 : i0);
           *st.h8(lane, 0) = make_uint4(ah[0], ah[1], ah[2], ah[3]);
@@ -572,7 +588,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             h[q + 3] = silu(fmaf(__uint_as_float(g[q + 3]), rstd, bg.w)) * fmaf(__uint_as_float(u[q + 3]), rstd, bu.w);
           }
           const int64_t off = static_cast<int64_t>(row0) * p.ld_out + n_blk * (BN / 2) + c;
-          emit_piece<SPLIT>(st, h, p.out_bf16 + off, p.out_lo + off, p.ld_out, rows_valid, lane, 16, of16);
+          emit_piece<SPLIT>(st, h, p.out_bf16 + off, p.out_lo + off, p.ld_out, rows_valid, lane, 16, of16, osat);
         }
       }
       // all of this warp's TMEM reads are complete (tcgen05.wait::ld above)

@@ -60,6 +60,11 @@ struct GemmArgs {
   float* tgt_logit;        // [M] acc[target] * inv_temp
   // EPI_QKV, CTA-pair kernel: the same angles indexed by position (plan.cuh pos_win / pos_tab); optional — without
   // them (or with more than 64 positions) the single-CTA kernel runs with the per-row tables
+  // f16 activation mode (GEMM_OUT_F16): device counter of conversions that saturated (null: not counted), and the
+  // largest norm_w^2 (EPI_RESID of the pair kernel: a row whose sum of squares times this stays below 65504^2 cannot
+  // saturate, so the element-wise scan only runs for rows that might)
+  unsigned int* sat;
+  float sat_wmax2;
   const int32_t* pos_win;  // [M] hpos | wpos << 16
   const float* pos_tab;    // [n_pos, 40]
   int n_pos;

@@ -398,6 +398,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
           }
           uint32_t pk[16];
+          const float ss_before = ss;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float4* xp = reinterpret_cast<float4*>(xrow + ((j ^ sx) << 4));
@@ -413,6 +414,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             *xp = f;                                                         // new residual, in place
             pk[2 * j] = pack16x2<V>(f.x * w.x, f.y * w.y);                   // next GEMM's operand: x * w_norm
             pk[2 * j + 1] = pack16x2<V>(f.z * w.z, f.w * w.w);
+          }
+          if constexpr (V == 1) {
+            // range guard: |x_c * w_c| <= sqrt(sum x^2) * max|w|, so a sub-step whose sum of squares times max w^2 stays
+            // below 65504^2 cannot have saturated; otherwise look for the saturated pattern in the packed halves
+            if (p.sat != nullptr && !((ss - ss_before) * p.sat_wmax2 < 4.29e9f)) {
+              bool hit = false;
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                hit |= (pk[j] & 0x7fffu) >= 0x7bffu || ((pk[j] >> 16) & 0x7fffu) >= 0x7bffu;
+              if (hit) atomicAdd(p.sat, 1u);
+            }
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -441,6 +453,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mbar_wait_relaxed(&acc_full[as], use & 1u);
         tc_fence_after();
         uint8_t* out_row = out_base + (cg * 2) * kBox + row * 80;
+        float amax = 0.f;   // f16 range guard (V == 1)
 #pragma unroll 1
         for (int i0 = 0; i0 < 40; i0 += 8) {
           uint32_t lo[8], hi[8];
@@ -481,10 +494,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               b[q] = nb;
             }
           }
+          if constexpr (V == 1) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) amax = fmaxf(amax, fmaxf(fabsf(a[q]), fabsf(b[q])));
+          }
           *reinterpret_cast<uint4*>(out_row + i0 * 2) =
               make_uint4(pack16x2<V>(a[0], a[1]), pack16x2<V>(a[2], a[3]), pack16x2<V>(a[4], a[5]), pack16x2<V>(a[6], a[7]));
           *reinterpret_cast<uint4*>(out_row + kBox + i0 * 2) =
               make_uint4(pack16x2<V>(b[0], b[1]), pack16x2<V>(b[2], b[3]), pack16x2<V>(b[4], b[5]), pack16x2<V>(b[6], b[7]));
+        }
+        if constexpr (V == 1) {
+          if (p.sat != nullptr && valid) sat_guard(amax, p.sat);
         }
         tc_fence_before();
         __syncwarp();
@@ -548,6 +568,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tc_fence_after();
         // 128B-swizzled [128 x 64 bf16] boxes: 16-byte chunk index XOR (row & 7), as TMA SWIZZLE_128B expects
         uint8_t* orow = out_base + (cg >> 1) * 16384 + row * 128;
+        float amax = 0.f;   // f16 range guard (V == 1)
 #pragma unroll
         for (int piece = 0; piece < 2; ++piece) {
           const int c = cg * 32 + piece * 16;
@@ -565,11 +586,18 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             h[q + 2] = silu(fmaf(__uint_as_float(g[q + 2]), rstd, bg.z)) * fmaf(__uint_as_float(u[q + 2]), rstd, bu.z);
             h[q + 3] = silu(fmaf(__uint_as_float(g[q + 3]), rstd, bg.w)) * fmaf(__uint_as_float(u[q + 3]), rstd, bu.w);
           }
+          if constexpr (V == 1) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) amax = fmaxf(amax, fabsf(h[q]));
+          }
           const int chunk = (cg & 1) * 4 + piece * 2;
           *reinterpret_cast<uint4*>(orow + (((chunk) ^ (row & 7)) << 4)) =
               make_uint4(pack16x2<V>(h[0], h[1]), pack16x2<V>(h[2], h[3]), pack16x2<V>(h[4], h[5]), pack16x2<V>(h[6], h[7]));
           *reinterpret_cast<uint4*>(orow + (((chunk + 1) ^ (row & 7)) << 4)) =
               make_uint4(pack16x2<V>(h[8], h[9]), pack16x2<V>(h[10], h[11]), pack16x2<V>(h[12], h[13]), pack16x2<V>(h[14], h[15]));
+        }
+        if constexpr (V == 1) {
+          if (p.sat != nullptr && valid) sat_guard(amax, p.sat);
         }
         tc_fence_before();
         __syncwarp();

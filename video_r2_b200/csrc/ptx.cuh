@@ -270,6 +270,12 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// Range guard of the f16 activation mode: `amax` is the largest |fp32 value| a thread is about to convert; anything
+// outside fp16's finite range saturates (cvt.rn.satfinite) and is counted, NaN included.  The host reads the counter
+// after the forward (vr2_tower_saturation_count) and re-runs the call in the split precision when it is non-zero.
+__device__ __forceinline__ void sat_guard(float amax, unsigned int* counter) {
+  if (!(amax <= 65504.0f)) atomicAdd(counter, 1u);
+}
 // 16-bit activation pair in the format the next contraction reads: F16 = 0 bf16, 1 fp16
 template <int F16>
 __device__ __forceinline__ uint32_t pack16x2(float lo, float hi) {

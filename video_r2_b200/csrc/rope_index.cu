@@ -69,7 +69,9 @@ __device__ int block_scan(int v, int* total, int* warp_sums) {
   return x + base;
 }
 
-// scratch layout: cidx [B,S] int32 (compact -> original position), counts [B,3] int32 (len, n_img, n_vid)
+// scratch layout: cidx [B,S] int32 (compact -> original position), counts [B,3] int32 (len, n_img, n_vid), then one
+// int32 error word (bit 0: a row names more images than image_grid_thw has rows / no image grid at all, bit 1: the same
+// for videos -- Hugging Face raises IndexError / TypeError there; vr2_rope_index_status reads it)
 __global__ void __launch_bounds__(kThreads)
 rope_compact_kernel(const int64_t* __restrict__ ids, const void* __restrict__ mask, int mask_dtype, int S,
                     int64_t vs_id, int64_t img_id, int64_t vid_id, int32_t* __restrict__ cidx,
@@ -79,6 +81,7 @@ rope_compact_kernel(const int64_t* __restrict__ ids, const void* __restrict__ ma
   const int b = blockIdx.x;
   const int64_t row = static_cast<int64_t>(b) * S;
   if (threadIdx.x == 0) { s_img = 0; s_vid = 0; }
+  if (b == 0 && threadIdx.x == 0) counts[gridDim.x * 3] = 0;   // error word, set by rope_fill_kernel
   int running = 0;
   for (int base = 0; base < S; base += kThreads) {
     const int i = base + threadIdx.x;
@@ -112,7 +115,7 @@ __global__ void __launch_bounds__(kThreads)
 rope_fill_kernel(const int64_t* __restrict__ ids, int B, int S, const int64_t* __restrict__ image_thw, int n_img_total,
                  const int64_t* __restrict__ video_thw, int n_vid_total, const float* __restrict__ spg_arr,
                  vr2_rope_config cfg, const int32_t* __restrict__ cidx, const int32_t* __restrict__ counts,
-                 int64_t* __restrict__ pos, int64_t* __restrict__ deltas) {
+                 int32_t* __restrict__ err, int64_t* __restrict__ pos, int64_t* __restrict__ deltas) {
   __shared__ int s_ed_img, s_ed_vid;
   const int b = blockIdx.x;
   const int64_t row = static_cast<int64_t>(b) * S;
@@ -158,13 +161,20 @@ rope_fill_kernel(const int64_t* __restrict__ ids, int B, int S, const int64_t* _
     int64_t t, h, w;
     float spg;
     int ed;
+    // A row that names an item the grids do not describe (grid pointer null / empty, or more items than grid rows):
+    // HF raises; here the item is not placed (no read through a null or out-of-range pointer), the rest of the row
+    // is numbered as text and the error word is set.  All operands are block-uniform, so the break is too.
+    if (ed_img < ed_vid ? (image_thw == nullptr || img_i >= n_img_total) : (video_thw == nullptr || vid_i >= n_vid_total)) {
+      if (threadIdx.x == 0) atomicOr(err, ed_img < ed_vid ? 1 : 2);
+      break;
+    }
     if (ed_img < ed_vid) {
-      const int64_t* g = image_thw + 3 * static_cast<int64_t>(min(img_i, max(n_img_total - 1, 0)));
+      const int64_t* g = image_thw + 3 * static_cast<int64_t>(img_i);
       t = g[0]; h = g[1]; w = g[2];
       spg = 0.f;
       ++img_i; --remain_img; ed = ed_img;
     } else {
-      const int vi = min(vid_i, max(n_vid_total - 1, 0));
+      const int vi = vid_i;
       const int64_t* g = video_thw + 3 * static_cast<int64_t>(vi);
       t = g[0]; h = g[1]; w = g[2];
       spg = spg_arr != nullptr ? spg_arr[vi] : 1.0f;
@@ -318,7 +328,17 @@ extern "C" int vr2_rope_index(const vr2_rope_config* cfg, const int64_t* ids, co
                                                    cfg->image_token_id, cfg->video_token_id, cidx, counts);
   VR2_CUDA(cudaGetLastError());
   rope_fill_kernel<<<B, kThreads, 0, stream>>>(ids, B, S, image_thw, n_img, video_thw, n_vid, spg, *cfg, cidx, counts,
-                                                pos, deltas);
+                                                counts + static_cast<size_t>(B) * 3, pos, deltas);
   VR2_CUDA(cudaGetLastError());
+  return VR2_OK;
+}
+
+extern "C" int vr2_rope_index_status(const void* scratch, int32_t B, int32_t S, int32_t* status_host, void* stream_v) {
+  if (scratch == nullptr || status_host == nullptr || B <= 0 || S <= 0)
+    return fail(VR2_ERR_ARG, "vr2_rope_index_status: null argument / empty shape");
+  cudaStream_t stream = as_stream(stream_v);
+  const int32_t* word = static_cast<const int32_t*>(scratch) + static_cast<size_t>(B) * S + static_cast<size_t>(B) * 3;
+  VR2_CUDA(cudaMemcpyAsync(status_host, word, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+  VR2_CUDA(cudaStreamSynchronize(stream));
   return VR2_OK;
 }

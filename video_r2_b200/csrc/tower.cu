@@ -69,6 +69,8 @@ struct vr2_tower {
   vr2::Tensor fc2_w, fc2_b;        // bf16 [out, md], fp32 [out]
   vr2::Tensor fc1_h, fc2_h;        // fp16 copies (VR2_PRECISION_F16)
   bool f16_ready = false;          // the fp16 copies reflect the current weights
+  unsigned int* sat = nullptr;     // device counter: fp16 conversions that saturated (f16 mode's range guard)
+  std::vector<float> norm_wmax2;   // [2 * depth + 1] largest squared weight of norm1[l], norm2[l], ..., ln_q (finalize)
   std::vector<void*> allocs;
   // optional per-kind CUDA-event timing (vr2_tower_profile)
   uint32_t prof_mask = 0;
@@ -175,6 +177,12 @@ extern "C" int vr2_tower_create(const vr2_tower_config* cfg, int32_t device, vr2
   if (e != cudaSuccess || n_dev <= device)
     return fail(VR2_ERR_CUDA, "vr2_tower_create: CUDA device %d not available (%s); there is no CPU path", device,
                 e != cudaSuccess ? cudaGetErrorString(e) : "device count too small");
+  // allocations below go to `device`; the caller's current device is restored on every exit path
+  struct DeviceGuard {
+    int prev = -1;
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  } guard;
+  VR2_CUDA(cudaGetDevice(&guard.prev));
   VR2_CUDA(cudaSetDevice(device));
   cudaDeviceProp prop;
   VR2_CUDA(cudaGetDeviceProperties(&prop, device));
@@ -210,6 +218,11 @@ extern "C" int vr2_tower_create(const vr2_tower_config* cfg, int32_t device, vr2
     A(&L.gu_b, 2 * ip * 4);
     A(&L.down_w, h * ip * 2);
     A(&L.down_b, h * 4);
+  }
+  if (rc == VR2_OK) {
+    Tensor c;
+    rc = alloc_zero(t, &c, 64);
+    t->sat = static_cast<unsigned int*>(c.ptr);
   }
   if (rc != VR2_OK) {
     vr2_tower_destroy(t);
@@ -315,6 +328,25 @@ extern "C" int vr2_tower_finalize(vr2_tower* t) {
     if (missing.size() > 600) missing = missing.substr(0, 600) + " ...";
     return fail(VR2_ERR_STATE, "vr2_tower_finalize: missing tensors: %s", missing.c_str());
   }
+  // largest squared RMSNorm weight per norm vector: the bound the residual epilogues' f16 range guard uses
+  {
+    const size_t h = t->cfg.hidden_size;
+    std::vector<float> buf(h);
+    auto wmax2 = [&](const Tensor& w, float* out) -> int {
+      VR2_CUDA(cudaMemcpy(buf.data(), w.ptr, h * sizeof(float), cudaMemcpyDeviceToHost));
+      float m = 0.f;
+      for (float v : buf) m = std::max(m, v * v);
+      *out = m;
+      return VR2_OK;
+    };
+    t->norm_wmax2.assign(2 * t->cfg.depth + 1, 0.f);
+    int rc;
+    for (int l = 0; l < t->cfg.depth; ++l) {
+      if ((rc = wmax2(t->layers[l].norm1_w, &t->norm_wmax2[2 * l])) != VR2_OK) return rc;
+      if ((rc = wmax2(t->layers[l].norm2_w, &t->norm_wmax2[2 * l + 1])) != VR2_OK) return rc;
+    }
+    if ((rc = wmax2(t->lnq_w, &t->norm_wmax2[2 * t->cfg.depth])) != VR2_OK) return rc;
+  }
   t->finalized = true;
   return VR2_OK;
 }
@@ -402,25 +434,25 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
     return fail(VR2_ERR_ARG, "vr2_tower_forward: workspace %zu < required %zu bytes", workspace_bytes, w.bytes);
   cudaStream_t s = as_stream(stream_v);
   const int h = t->cfg.hidden_size;
+  // ---- precision of this call
+  int rc0 = VR2_OK;
+  const bool split = t->precision == VR2_PRECISION_SPLIT;
+  // f16 activation mode: every 16-bit activation buffer (xb, qkv, att, h, the merger's intermediates) holds fp16 instead
+  // of bf16 and the GEMMs read fp16 copies of the weights (ensure_f16_weights); the patch-embed GEMM multiplies the
+  // caller's bf16 pixels with the bf16 weight as before.  Conversions that saturate are counted in t->sat.
+  const bool f16 = t->precision == VR2_PRECISION_F16;
   int parts = 0;  // sum-of-squares partials per row written by the most recent EPI_RESID launch
   const float eps = t->cfg.rms_norm_eps;
   const char* msg = "";
-  auto G = [&](const GemmArgs& a, int kind, const char* what) -> int {
+  auto G = [&](GemmArgs& a, int kind, const char* what) -> int {
     ProfScope prof(t, kind, s);
+    a.sat = f16 ? t->sat : nullptr;
     if (a.epilogue == EPI_RESID) parts = gemm_resid_parts(a);
     cudaError_t e = gemm_launch(a, t->num_sms, s, &msg);
     if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? VR2_ERR_ARG : VR2_ERR_CUDA, "vr2_tower_forward: %s: %s %s", what, cudaGetErrorString(e), msg);
     return VR2_OK;
   };
   int rc;
-
-  // ---- patch embed (Conv3d with kernel == stride == a [N,1176] x [1176,1280] GEMM), stored window-permuted
-  int rc0 = VR2_OK;
-  const bool split = t->precision == VR2_PRECISION_SPLIT;
-  // f16 activation mode: every 16-bit activation buffer (xb, qkv, att, h, the merger's intermediates) holds fp16 instead
-  // of bf16 and the GEMMs read fp16 copies of the weights (ensure_f16_weights); the patch-embed GEMM multiplies the
-  // caller's bf16 pixels with the bf16 weight as before
-  const bool f16 = t->precision == VR2_PRECISION_F16;
   const int act_in = f16 ? GEMM_A_F16 : 0, act_out = f16 ? GEMM_OUT_F16 : 0;
   if (f16 && (rc0 = ensure_f16_weights(t, s)) != VR2_OK) return rc0;
   auto WT = [&](const Tensor& w_bf16, const Tensor& w_f16) { return static_cast<const __nv_bfloat16*>(f16 ? w_f16.ptr : w_bf16.ptr); };
@@ -440,6 +472,7 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
     a.x = w.x; a.ldx = h; a.out_bf16 = w.xb; a.out_lo = w.xb_lo; a.ld_out = h;
     a.row_map = plan->row_map;
     a.norm_w = static_cast<const float*>(t->layers[0].norm1_w.ptr);
+    a.sat_wmax2 = t->norm_wmax2[0];
     a.ssq = w.ssq;
     if ((rc = G(a, VR2_K_PATCH_EMBED, "patch_embed")) != VR2_OK) return rc;
   }
@@ -477,6 +510,7 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
       a.bias = static_cast<const float*>(L.proj_b.ptr);
       a.x = w.x; a.ldx = h; a.out_bf16 = w.xb; a.out_lo = w.xb_lo; a.ld_out = h;
       a.norm_w = static_cast<const float*>(L.norm2_w.ptr);
+      a.sat_wmax2 = t->norm_wmax2[2 * l + 1];
       a.ssq = w.ssq;
       if ((rc = G(a, VR2_K_PROJ, "proj")) != VR2_OK) return rc;
     }
@@ -498,6 +532,7 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
       a.bias = static_cast<const float*>(L.down_b.ptr);
       a.x = w.x; a.ldx = h; a.out_bf16 = w.xb; a.out_lo = w.xb_lo; a.ld_out = h;
       a.norm_w = static_cast<const float*>(l + 1 < t->cfg.depth ? t->layers[l + 1].norm1_w.ptr : t->lnq_w.ptr);
+      a.sat_wmax2 = t->norm_wmax2[2 * l + 2];
       a.ssq = w.ssq;
       if ((rc = G(a, VR2_K_DOWN, "down")) != VR2_OK) return rc;
     }
@@ -508,7 +543,8 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
   const int md = t->merge_dim;
   {
     ProfScope prof(t, VR2_K_MERGER_NORM, s);
-    VR2_CUDA(rmsnorm_to_bf16(w.x, static_cast<const float*>(t->lnq_w.ptr), w.qkv, w.qkv_lo, N, h, eps, s, f16));
+    VR2_CUDA(rmsnorm_to_bf16(w.x, static_cast<const float*>(t->lnq_w.ptr), w.qkv, w.qkv_lo, N, h, eps, s, f16,
+                             f16 ? t->sat : nullptr));
   }
   {
     GemmArgs a{};
@@ -562,6 +598,23 @@ extern "C" int vr2_tower_set_precision(vr2_tower* t, int32_t precision) {
 }
 
 extern "C" int32_t vr2_tower_get_precision(const vr2_tower* t) { return t == nullptr ? -1 : t->precision; }
+
+extern "C" int vr2_tower_saturation_snapshot(vr2_tower* t, uint32_t* dst, void* stream_v) {
+  if (t == nullptr || dst == nullptr) return fail(VR2_ERR_ARG, "vr2_tower_saturation_snapshot: null argument");
+  VR2_CUDA(cudaMemcpyAsync(dst, t->sat, sizeof(uint32_t), cudaMemcpyDefault, as_stream(stream_v)));
+  return VR2_OK;
+}
+
+extern "C" int vr2_tower_saturation_count(vr2_tower* t, uint64_t* count_host, int32_t reset, void* stream_v) {
+  if (t == nullptr || count_host == nullptr) return fail(VR2_ERR_ARG, "vr2_tower_saturation_count: null argument");
+  cudaStream_t s = as_stream(stream_v);
+  unsigned int v = 0;
+  VR2_CUDA(cudaMemcpyAsync(&v, t->sat, sizeof(v), cudaMemcpyDeviceToHost, s));
+  if (reset) VR2_CUDA(cudaMemsetAsync(t->sat, 0, sizeof(v), s));
+  VR2_CUDA(cudaStreamSynchronize(s));
+  *count_host = v;
+  return VR2_OK;
+}
 
 extern "C" int vr2_tower_profile(vr2_tower* t, uint32_t kind_mask) {
   if (t == nullptr) return fail(VR2_ERR_ARG, "vr2_tower_profile: null tower");

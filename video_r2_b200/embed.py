@@ -78,20 +78,48 @@ def scatter_rows(src: torch.Tensor, dst: torch.Tensor, dest_rows: torch.Tensor) 
     return dst
 
 
-@torch.no_grad()
+class _PlaceVisual(torch.autograd.Function):
+    """`inputs_embeds.masked_scatter(mask, feats)` for a graph-attached `inputs_embeds` (trainable `embed_tokens`,
+    train_grpo.sh): out of place like the reference, and the gradient at the visual rows is CUT — masked_scatter
+    routes those rows' gradient to `feats` (a frozen tower: dropped), never to the embedding table."""
+
+    @staticmethod
+    def forward(ctx, inputs_embeds, tower, pixel_values, plan, rows):
+        out = inputs_embeds.detach().clone()
+        tower.forward_into(pixel_values, plan, out, rows)
+        ctx.save_for_backward(rows)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        (rows,) = ctx.saved_tensors
+        g = grad.contiguous().clone()
+        zeros = torch.zeros((rows.numel(), g.shape[-1]), dtype=g.dtype, device=g.device)
+        scatter_rows(zeros, g, rows)         # rows of -1 (no such token) are skipped by the kernel
+        return g, None, None, None, None
+
+
 def embed_visual_tokens(tower, inputs_embeds: torch.Tensor, input_ids: torch.Tensor, token_id: int,
                         pixel_values: torch.Tensor, grid_thw, what: str = "Video") -> torch.Tensor:
-    """In-place equivalent of the reference's tower call + masked_scatter for one modality.  inputs_embeds [B, S, D]
-    contiguous (bf16 / fp32, D == tower out_hidden_size), input_ids [B, S].  Raises the reference's ValueError when
-    the number of pad tokens differs from the number of visual features."""
+    """The reference's tower call + token count check + masked_scatter for one modality
+    (monkey_patch_forward.py:392-406).  inputs_embeds [B, S, D] contiguous (bf16 / fp32, D == tower out_hidden_size),
+    input_ids [B, S].
+
+    The count check runs FIRST (one small stream compaction + the same host wait as the reference's
+    `.sum().item()`), so a token / feature mismatch raises the reference's ValueError before anything is written.
+    Without a graph (`inputs_embeds` detached: generation, frozen embeddings) the visual rows are stored IN PLACE into
+    `inputs_embeds` from the merger's last GEMM and the same tensor is returned.  With grad enabled and
+    `inputs_embeds.requires_grad` the result is a new tensor (as `masked_scatter` returns) whose backward passes the
+    gradient through at text rows and zeroes it at visual rows."""
     if not inputs_embeds.is_contiguous() or inputs_embeds.shape[-1] != tower.cfg.out_hidden_size:
         raise ValueError("embed_visual_tokens: inputs_embeds must be contiguous [..., out_hidden_size]")
     plan = tower.plan(grid_thw)
     pos = token_positions_async(input_ids, token_id, capacity=plan.num_tokens)
-    # the tower is enqueued before the host learns the count (the reference's `.sum().item()` also waits for the GPU,
-    # but with nothing queued behind it); destinations that do not exist are -1 and are skipped by the store
-    tower.forward_into(pixel_values, plan, inputs_embeds, pos.rows)
     count = pos.count()
     if count != plan.num_tokens:
         raise ValueError(f"{what} features and {what.lower()} tokens do not match: tokens: {count}, features {plan.num_tokens}")
+    if torch.is_grad_enabled() and inputs_embeds.requires_grad:
+        return _PlaceVisual.apply(inputs_embeds, tower, pixel_values, plan, pos.rows)
+    with torch.no_grad():
+        tower.forward_into(pixel_values, plan, inputs_embeds, pos.rows)
     return inputs_embeds

@@ -9,10 +9,25 @@ from ._lib import check, lib
 from .tower import _stream_ptr
 
 
-@torch.no_grad()
 def lm_logprob(hidden: torch.Tensor, weight: torch.Tensor, target: torch.Tensor, temperature: float = 1.0) -> torch.Tensor:
     """hidden [..., K] bf16, weight [V, K] bf16 (lm_head.weight), target [...] int64 -> fp32 [...]:
-    log_softmax(hidden @ weight.T / temperature, -1).gather(-1, target)."""
+    log_softmax(hidden @ weight.T / temperature, -1).gather(-1, target).
+
+    FORWARD ONLY.  It serves the passes of GRPO that run without a graph — the reference-policy and old-policy
+    log-probabilities (grpo_trainer.py:813-833, under `torch.no_grad()` / `inference_mode`) and evaluation.  The
+    policy pass that the loss back-propagates through (grpo_trainer.py:1094-1096) needs d logp / d hidden and
+    d logp / d lm_head, which this kernel does not produce: calling it there would silently cut the gradient, so a
+    call with grad enabled on an input that requires grad raises instead."""
+    if torch.is_grad_enabled() and (hidden.requires_grad or weight.requires_grad):
+        raise RuntimeError(
+            "lm_logprob is forward-only (no backward kernel): call it under torch.no_grad() for the reference / "
+            "old-policy passes, and keep `selective_log_softmax(model(...).logits / T, ids)` for the pass the loss "
+            "differentiates")
+    with torch.no_grad():
+        return _lm_logprob(hidden, weight, target, temperature)
+
+
+def _lm_logprob(hidden, weight, target, temperature):
     if not (hidden.is_cuda and weight.is_cuda) or hidden.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
         raise ValueError("lm_logprob: hidden and weight must be bfloat16 CUDA tensors")
     K = hidden.shape[-1]

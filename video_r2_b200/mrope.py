@@ -11,11 +11,40 @@ from ._lib import VR2_BF16, VR2_F32, check, lib
 from .tower import _stream_ptr
 
 
-@torch.no_grad()
+class _MropeFn(torch.autograd.Function):
+    """The rotation is orthogonal per channel pair, so its vector-Jacobian product is the rotation by the NEGATED
+    angle: the same kernel on the incoming gradients with negated position ids (cos is even, sin is odd — exact)."""
+
+    @staticmethod
+    def forward(ctx, q, k, position_ids, inv_freq, mrope_section, attention_scaling):
+        ctx.save_for_backward(position_ids, inv_freq)
+        ctx.sec, ctx.scaling = mrope_section, attention_scaling
+        return _apply(q, k, position_ids, inv_freq, mrope_section, attention_scaling, False)
+
+    @staticmethod
+    def backward(ctx, gq, gk):
+        position_ids, inv_freq = ctx.saved_tensors
+        dq, dk = _apply(gq.contiguous(), gk.contiguous(), -position_ids, inv_freq, ctx.sec, ctx.scaling, False)
+        return dq, dk, None, None, None, None
+
+
 def apply_mrope(q: torch.Tensor, k: torch.Tensor, position_ids: torch.Tensor, inv_freq: torch.Tensor,
                 mrope_section=(16, 24, 24), attention_scaling: float = 1.0, inplace: bool = False):
     """q [B, Hq, S, D], k [B, Hk, S, D] (bf16 or fp32, CUDA), position_ids [3, B, S] int64, inv_freq [D/2] fp32.
-    -> (q_embed, k_embed), same shapes and dtype, equal to HF's result in that dtype."""
+    -> (q_embed, k_embed), same shapes and dtype, equal to HF's result in that dtype.
+
+    Differentiable with respect to q and k (training paths: `Qwen2_5_VLAttention.forward` with a trainable LLM or
+    LoRA on q_proj / k_proj, train_grpo.sh `freeze_llm False`): under autograd the call goes through `_MropeFn`,
+    whose backward is the inverse rotation by the same kernel.  `inplace=True` is refused when a gradient is needed."""
+    if torch.is_grad_enabled() and (q.requires_grad or k.requires_grad):
+        if inplace:
+            raise RuntimeError("apply_mrope(inplace=True) would overwrite tensors autograd needs; use inplace=False when training")
+        return _MropeFn.apply(q, k, position_ids, inv_freq, tuple(int(v) for v in mrope_section), float(attention_scaling))
+    return _apply(q, k, position_ids, inv_freq, mrope_section, attention_scaling, inplace)
+
+
+@torch.no_grad()
+def _apply(q, k, position_ids, inv_freq, mrope_section, attention_scaling, inplace):
     if not (q.is_cuda and k.is_cuda) or q.dtype != k.dtype or q.dtype not in (torch.float32, torch.bfloat16):
         raise ValueError("apply_mrope: q and k must be CUDA tensors of the same dtype (float32 or bfloat16)")
     if q.dim() != 4 or k.dim() != 4 or q.shape[0] != k.shape[0] or q.shape[2:] != k.shape[2:]:

@@ -7,8 +7,8 @@ forwards (train/src/train/monkey_patch_forward.py:22-26,
 
 After install():
   * `Qwen2_5_VisionTransformerPretrainedModel.forward(hidden_states, grid_thw)` runs libvr2.so.
-    The first call on a module instance snapshots its weights (`state_dict()`) into library-owned,
-    repacked storage — valid because every shipped Video-R2 recipe freezes the tower
+    The first call on a module instance snapshots its weights (`state_dict()`, all-gathered first when
+    DeepSpeed ZeRO-3 has partitioned them: `full_parameters`) into library-owned, repacked storage — valid because every shipped Video-R2 recipe freezes the tower
     (train_sft.sh:42-44, train_grpo.sh:47-49); call `vr2.refresh(module)` after changing weights.
     Return type follows the installed transformers: a bare Tensor on 4.x (what
     monkey_patch_forward.py:392 expects), `BaseModelOutputWithPooling(pooler_output=...)` on >= 5.
@@ -20,6 +20,8 @@ After install():
 """
 from __future__ import annotations
 
+import contextlib
+
 import torch
 
 from .rope_index import RopeConfig, get_rope_index
@@ -27,7 +29,36 @@ from .tower import VisionConfig, VisionTower
 
 _ORIGINALS = {}
 _REUSE = 0   # install(reuse_embeddings=n): keep the last n tower outputs per module (see VisionTower.forward)
-_PRECISION = None   # install(precision=...): operand precision of the towers built from now on (None: $VR2_PRECISION / bf16)
+_PRECISION = None   # install(precision=...): operand precision of the towers built from now on (None: $VR2_PRECISION / auto)
+
+
+def _is_zero3_partitioned(p) -> bool:
+    """DeepSpeed ZeRO-3 (`zero.Init`, what `from_pretrained` runs under with zero3.json) replaces every parameter's
+    storage with an empty placeholder and hangs the rank's shard off `ds_tensor`; `ds_id` marks such a parameter."""
+    return hasattr(p, "ds_id") or hasattr(p, "ds_tensor")
+
+
+@contextlib.contextmanager
+def full_parameters(module):
+    """Context in which `module.state_dict()` holds the FULL weights.  A no-op for ordinary modules.  Under ZeRO-3
+    (both shipped Video-R2 recipes: train/scripts/train_sft.sh:29, train_grpo.sh:42 -> zero3.json:16-27) the
+    parameters of every sub-module are partitioned and DeepSpeed's pre-forward hook gathers only the parameters of
+    the module whose `forward` runs -- this patch replaces the tower's forward wholesale, so the blocks' hooks never
+    fire; all of the tower's parameters are therefore all-gathered here once (a collective: every rank reaches the
+    first `self.visual(...)` call, which is what the reference's dummy-image path guarantees,
+    monkey_patch_forward.py:358-369), copied into the library's own storage, and released again."""
+    params = [p for p in module.parameters() if _is_zero3_partitioned(p)]
+    if not params:
+        yield
+        return
+    try:
+        import deepspeed
+    except ImportError as e:  # partitioned parameters without deepspeed cannot be gathered: say so instead of
+        raise RuntimeError(   # handing empty placeholders to the library
+            "video_r2_b200: the vision tower's parameters are ZeRO-3 partitioned (ds_id present) but `deepspeed` "
+            "is not importable, so they cannot be gathered") from e
+    with deepspeed.zero.GatheredParameters(params, modifier_rank=None):
+        yield
 
 
 def _tower_of(module) -> VisionTower:
@@ -35,7 +66,9 @@ def _tower_of(module) -> VisionTower:
     dev = next(module.parameters()).device
     if tw is None or tw.device != dev:
         cfg = VisionConfig.from_hf(module.config)
-        tw = VisionTower(cfg, module.state_dict(), device=dev, precision=_PRECISION)
+        with full_parameters(module):
+            # VisionTower copies (and repacks) every tensor into library-owned storage before returning
+            tw = VisionTower(cfg, module.state_dict(), device=dev, precision=_PRECISION)
         module.__dict__["_vr2_tower"] = tw
     return tw
 
@@ -86,13 +119,14 @@ def install(visual: bool = True, rope_index: bool = True, reuse_embeddings: int 
     """Patch the Hugging Face classes in place.  Idempotent.  reuse_embeddings=n keeps the last n tower outputs and
     returns them when the same (unmodified) pixel tensor object is encoded again — GRPO encodes each clip three times
     per step with a frozen tower; off by default because the returned tensor is then shared between calls.
-    precision: "bf16" | "f16" | "split" for the towers built after this call (include/vr2.h vr2_precision; default
-    $VR2_PRECISION, else bf16)."""
+    precision: "auto" | "f16" | "split" | "bf16" for the towers built after this call (see VisionTower; default
+    $VR2_PRECISION, else "auto": fp16 activations with the saturation guard and an automatic split re-run, the mode
+    that meets the north-star tolerance max-abs 2e-2 / cosine 0.9995 against the fp32 reference)."""
     from transformers.models.qwen2_5_vl import modeling_qwen2_5_vl as M
     from . import _lib, lib
     global _REUSE, _PRECISION
-    if precision is not None and precision not in _lib.PRECISIONS:
-        raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}, got {precision!r}")
+    if precision is not None and precision not in _lib.HOST_PRECISIONS:
+        raise ValueError(f"precision must be one of {sorted(_lib.HOST_PRECISIONS)}, got {precision!r}")
     _REUSE = int(reuse_embeddings)
     _PRECISION = precision
     lib()  # fail now, loudly, if libvr2.so is missing

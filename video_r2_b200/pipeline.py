@@ -23,6 +23,8 @@ from .rope_index import get_rope_index
 
 
 class HostPipeline:
+    _SNAPS = 256   # guard snapshots kept (= batches that may be in flight)
+
     def __init__(self, tower, depth: int = 2, rope_config=None):
         if depth < 1:
             raise ValueError("depth must be >= 1")
@@ -41,6 +43,14 @@ class HostPipeline:
         self._d2h_done = [None] * depth
         self._pending = collections.deque()
         self._n = 0
+        # f16 range guard (tower precision "auto" / "f16"): the counter is snapshotted behind every forward into pinned
+        # host memory; results() compares neighbouring snapshots and repeats a clamped batch in the split precision
+        self._guard = tower.precision in ("auto", "f16")
+        self._snap = torch.zeros(self._SNAPS, dtype=torch.int32).pin_memory() if self._guard else None   # ring, one per submit
+        self._snap_seen = 0
+        if self._guard:
+            tower.saturation_count(reset=True)
+        self.fallbacks = 0
 
     def _buf(self, store, slot, shape, dtype):
         b = store[slot]
@@ -107,7 +117,11 @@ class HostPipeline:
             patchify(x_dev, patch_size=cfg.patch_size, temporal_patch_size=cfg.temporal_patch_size,
                      merge_size=cfg.spatial_merge_size, out=pix)
             x_dev = pix
-        self.tower.forward(x_dev, plan, out=out_dev)
+        self.tower.forward(x_dev, plan, out=out_dev, check_guard=False)
+        if self._guard:
+            if len(self._pending) >= self._SNAPS:
+                raise RuntimeError(f"HostPipeline: more than {self._SNAPS} batches in flight; consume results()")
+            self.tower.saturation_snapshot(self._snap[(self._n - 1) % self._SNAPS:])
         pos_dev = None
         if ids_dev is not None:
             kw = {"config": self.rope_config} if self.rope_config is not None else {}
@@ -129,13 +143,35 @@ class HostPipeline:
             d2h = torch.cuda.Event()
             d2h.record(self.s_out)
         self._d2h_done[slot] = d2h
-        self._pending.append((d2h, out_host, pos_host))
+        self._pending.append((d2h, out_host, pos_host, (self._n - 1) % self._SNAPS, (x_host, plan, _frames, _size)))
+
+    @torch.no_grad()
+    def _redo_split(self, out_host, x_host, plan, frames, size):
+        """Rare path: the f16 guard tripped on this batch.  Recompute it from the host input, synchronously, with
+        hi+lo bf16 operands, and overwrite its host result."""
+        self.fallbacks += 1
+        cfg = self.tower.cfg
+        x = x_host.to(self.dev)
+        if frames:
+            if size is not None:
+                x = resize_frames(x, size)
+            x = patchify(x.contiguous(), patch_size=cfg.patch_size, temporal_patch_size=cfg.temporal_patch_size,
+                         merge_size=cfg.spatial_merge_size)
+        out = torch.empty((plan.num_tokens, cfg.out_hidden_size), dtype=out_host.dtype, device=self.dev)
+        self.tower.run_split(plan, x.contiguous(), out)
+        out_host.copy_(out)
+        torch.cuda.current_stream(self.dev).synchronize()
 
     def results(self):
         """Yields (embeddings_host, position_ids_host or None) in submission order."""
         while self._pending:
-            ev, out_host, pos_host = self._pending.popleft()
+            ev, out_host, pos_host, snap_i, redo = self._pending.popleft()
             ev.synchronize()
+            if self._guard:
+                seen = int(self._snap[snap_i].item())   # cumulative counter right behind this batch's forward
+                if seen != self._snap_seen:
+                    self._snap_seen = seen
+                    self._redo_split(out_host, *redo)
             yield out_host, pos_host
 
     def drain(self):

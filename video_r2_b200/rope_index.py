@@ -37,8 +37,12 @@ def _default_int_cast(cfg: RopeConfig) -> bool:
 
 
 def get_rope_index(input_ids, image_grid_thw=None, video_grid_thw=None, second_per_grid_ts=None,
-                   attention_mask=None, *, config: RopeConfig = RopeConfig()):
-    """Returns (position_ids int64 [3,B,S], mrope_position_deltas int64 [B,1]) on input_ids' device."""
+                   attention_mask=None, *, config: RopeConfig = RopeConfig(), validate: bool = False):
+    """Returns (position_ids int64 [3,B,S], mrope_position_deltas int64 [B,1]) on input_ids' device.
+
+    validate=True waits for the kernels and raises ValueError when a row names more images / videos than the grid
+    tensors describe (Hugging Face raises IndexError there).  Off by default: the call then never synchronises, and
+    such a row is numbered without the missing item (the kernels never read past the grids)."""
     ref = input_ids if input_ids is not None else attention_mask
     if ref is None:
         raise ValueError("get_rope_index needs input_ids or attention_mask")
@@ -87,4 +91,11 @@ def get_rope_index(input_ids, image_grid_thw=None, video_grid_thw=None, second_p
         check(lib().vr2_rope_index(C.byref(rc), p(ids), p(mask), mcode, B, S, p(img), n_img, p(vid), n_vid, p(spg),
                                    scratch.data_ptr(), pos.data_ptr(), deltas.data_ptr(),
                                    torch.cuda.current_stream(dev).cuda_stream), "vr2_rope_index")
+        if validate and ids is not None and (img is not None or vid is not None) and B > 0 and S > 0:
+            st = C.c_int32(0)
+            check(lib().vr2_rope_index_status(scratch.data_ptr(), B, S, C.byref(st),
+                                              torch.cuda.current_stream(dev).cuda_stream), "vr2_rope_index_status")
+            if st.value:
+                what = " and ".join(n for bit, n in ((1, "image_grid_thw"), (2, "video_grid_thw")) if st.value & bit)
+                raise ValueError(f"get_rope_index: input_ids name more vision items than {what} describes")
     return pos, deltas

@@ -12,6 +12,7 @@ import collections
 import ctypes as C
 import dataclasses
 import os
+import warnings
 import weakref
 
 import torch
@@ -154,10 +155,15 @@ class VisionTower:
     ("patch_embed.proj.weight", "blocks.0.attn.qkv.weight", ...), fp32 or bf16, any device."""
 
     def __init__(self, cfg: VisionConfig, state_dict, device="cuda:0", plan_cache: int = 16, precision=None):
-        """precision: "bf16" (default; activations rounded to bf16 once per GEMM input, as HF's bf16 path),
-        "f16" (activations rounded to fp16 instead — 8x finer, same speed, fp16 copies of the weights (+1.35 GB);
-        meets max-abs 2e-2 against the fp32 reference; saturates at +-65504) or "split" (hi + lo bf16 operands, ~16 mantissa bits,
-        2x the MMA work; also meets 2e-2, no range limit).  Default comes from $VR2_PRECISION."""
+        """precision:
+          "auto"  (default) fp16 activations with the library's saturation guard: every forward is followed by a read of
+                  the guard counter (one 4-byte D2H + stream synchronisation, where HF's own forward has its `.tolist()`
+                  syncs) and is re-run in "split" if any activation left fp16's range.  Full speed and max-abs <= 2e-2
+                  against the fp32 reference on in-range activations; never silently clamped on outliers.
+          "f16"   the same arithmetic without the read: the caller checks `saturation_count()` itself (pipelines, benchmarks).
+          "split" hi + lo bf16 operands (~16 mantissa bits, bf16's range, 2x the MMA work); also meets 2e-2.
+          "bf16"  activations rounded to bf16 once per GEMM input, as HF's own bf16 path (max-abs ~5e-2 after 32 blocks).
+        Default comes from $VR2_PRECISION."""
         self.cfg = cfg
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -181,18 +187,35 @@ class VisionTower:
         self._plans = collections.OrderedDict()
         self._plan_cache = plan_cache
         self._ws = None
+        self._ws_split = None          # workspace of the split fallback (twice the size), kept once allocated
         self._emb_cache = collections.OrderedDict()   # embedding reuse, see forward(reuse=...)
         self.reuse_hits = 0
-        self.set_precision(precision or os.environ.get("VR2_PRECISION", "bf16"))
+        self.fallbacks = 0             # "auto": forwards repeated in split because the f16 guard tripped
+        self.set_precision(precision or os.environ.get("VR2_PRECISION", "auto"))
         self.load_state_dict(state_dict)
 
     def set_precision(self, precision: str):
-        if precision not in _lib.PRECISIONS:
-            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}, got {precision!r}")
-        check(lib().vr2_tower_set_precision(self._h, _lib.PRECISIONS[precision]), "vr2_tower_set_precision")
+        if precision not in _lib.HOST_PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.HOST_PRECISIONS)}, got {precision!r}")
+        check(lib().vr2_tower_set_precision(self._h, _lib.HOST_PRECISIONS[precision]), "vr2_tower_set_precision")
         self.precision = precision
         self._ws = None
         self._emb_cache.clear()
+
+    def saturation_count(self, reset: bool = True) -> int:
+        """f16 range guard: how many epilogue conversions met a value outside fp16's finite range since the last reset,
+        over everything enqueued on the current stream (synchronises it).  0 = nothing was clamped."""
+        n = C.c_uint64(0)
+        with torch.cuda.device(self.device):
+            check(lib().vr2_tower_saturation_count(self._h, C.byref(n), 1 if reset else 0, _stream_ptr(self.device)),
+                  "vr2_tower_saturation_count")
+        return int(n.value)
+
+    def saturation_snapshot(self, dst: torch.Tensor):
+        """Copies the guard counter into dst[0] (uint32/int32 tensor, pinned host or device) in stream order, no sync."""
+        with torch.cuda.device(self.device):
+            check(lib().vr2_tower_saturation_snapshot(self._h, dst.data_ptr(), _stream_ptr(self.device)),
+                  "vr2_tower_saturation_snapshot")
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -245,7 +268,8 @@ class VisionTower:
 
     # ------------------------------------------------------------------ forward
     @torch.no_grad()
-    def forward(self, hidden_states: torch.Tensor, grid_thw, out_dtype=None, out=None, reuse: int = 0) -> torch.Tensor:
+    def forward(self, hidden_states: torch.Tensor, grid_thw, out_dtype=None, out=None, reuse: int = 0,
+                check_guard=None) -> torch.Tensor:
         """hidden_states: [N, 1176] fp32/bf16 on this tower's device.  Returns [N/4, out_hidden].
 
         reuse > 0 keeps the last `reuse` results and returns the cached tensor when the SAME tensor object, unmodified
@@ -279,14 +303,48 @@ class VisionTower:
         odt = out_dtype or x.dtype
         if out is None:
             out = torch.empty((plan.num_tokens, self.cfg.out_hidden_size), dtype=odt, device=self.device)
+        self._launch(plan, x, out, None, check_guard)
+        return out
+
+    def _enqueue(self, plan, x, out, rows):
         ws = self._workspace(plan.num_patches)
         base = ws.data_ptr()
         aligned = (base + 1023) & ~1023
         with torch.cuda.device(self.device):
-            check(lib().vr2_tower_forward(self._h, plan._h, x.data_ptr(), _dtype_code(x.dtype), out.data_ptr(),
-                                          _dtype_code(out.dtype), aligned, ws.numel() - (aligned - base),
-                                          _stream_ptr(self.device)), "vr2_tower_forward")
-        return out
+            if rows is None:
+                check(lib().vr2_tower_forward(self._h, plan._h, x.data_ptr(), _dtype_code(x.dtype), out.data_ptr(),
+                                              _dtype_code(out.dtype), aligned, ws.numel() - (aligned - base),
+                                              _stream_ptr(self.device)), "vr2_tower_forward")
+            else:
+                check(lib().vr2_tower_forward_scatter(self._h, plan._h, x.data_ptr(), _dtype_code(x.dtype), out.data_ptr(),
+                                                      _dtype_code(out.dtype), out.shape[-1], rows.data_ptr(), aligned,
+                                                      ws.numel() - (aligned - base), _stream_ptr(self.device)),
+                      "vr2_tower_forward_scatter")
+
+    def _launch(self, plan, x, out, rows, check_guard=None):
+        """One forward (plain or scattered store).  In the "auto" precision the f16 guard counter is read behind it and
+        the call repeated in split when it is non-zero (the same destination rows are simply overwritten)."""
+        self._enqueue(plan, x, out, rows)
+        if check_guard is None:
+            check_guard = self.precision == "auto"
+        if check_guard and self.saturation_count(reset=True):
+            self.run_split(plan, x, out, rows)
+
+    def run_split(self, plan, x, out, rows=None):
+        """Repeat a forward in the split precision (fallback of the f16 range guard), then return to the current one."""
+        self.fallbacks += 1
+        if self.fallbacks == 1:
+            warnings.warn("video_r2_b200: activations left fp16's range (saturation guard tripped); this forward was "
+                          "repeated with hi+lo bf16 operands.  If it happens on every call, use precision='split'.")
+        keep, keep_ws = self.precision, self._ws
+        try:
+            check(lib().vr2_tower_set_precision(self._h, _lib.PRECISIONS["split"]), "vr2_tower_set_precision")
+            self._ws = self._ws_split
+            self._enqueue(plan, x, out, rows)
+            self._ws_split = self._ws
+        finally:
+            check(lib().vr2_tower_set_precision(self._h, _lib.HOST_PRECISIONS[keep]), "vr2_tower_set_precision")
+            self._ws = keep_ws
 
     __call__ = forward
 
@@ -308,14 +366,7 @@ class VisionTower:
         rows = dest_rows.to(device=self.device, dtype=torch.int32).contiguous()
         if rows.numel() != plan.num_tokens:
             raise ValueError(f"dest_rows has {rows.numel()} entries for {plan.num_tokens} visual tokens")
-        ws = self._workspace(plan.num_patches)
-        base = ws.data_ptr()
-        aligned = (base + 1023) & ~1023
-        with torch.cuda.device(self.device):
-            check(lib().vr2_tower_forward_scatter(self._h, plan._h, x.data_ptr(), _dtype_code(x.dtype), dest.data_ptr(),
-                                                  _dtype_code(dest.dtype), dest.shape[-1], rows.data_ptr(), aligned,
-                                                  ws.numel() - (aligned - base), _stream_ptr(self.device)),
-                  "vr2_tower_forward_scatter")
+        self._launch(plan, x, dest, rows)
         return dest
 
     KERNEL_KINDS = ("cast", "patch_embed", "qkv", "attn_window", "attn_full", "proj", "gate_up", "down",
