@@ -36,6 +36,28 @@ TEXT_BEFORE, TEXT_AFTER = 32, 64
 FLOP_PER_TOKEN = 5.261e9     # BASELINE.md §3 (dense layers + attention, algorithmic)
 
 
+# BASELINE.json configs beside the headline (configs[1]); grids are [t, h, w] in patches (t = frames / 2, h = H / 14)
+CFG5_CLIPS = [(16, 448, 448), (32, 448, 448), (64, 448, 448), (128, 336, 588), (8, 280, 504), (32, 280, 504), (128, 280, 504),
+              (16, 336, 588), (64, 336, 588), (4, 448, 448), (32, 392, 392), (64, 224, 392), (16, 504, 280), (128, 224, 224),
+              (2, 392, 392), (48, 364, 644)]          # the fixed ragged list (frames, H, W)
+SIDE_CONFIGS = {
+    "cfg1_16f_448": [[8, 32, 32]],
+    "cfg3_rollout_8x64f_448": [[32, 32, 32]] * 8,
+    "cfg4_128f_336x588": [[64, 24, 42]],
+    "cfg5_ragged_16_clips": [[f // 2, H // 14, W // 14] for f, H, W in CFG5_CLIPS],
+}
+
+
+def grid_flops(grid) -> float:
+    """Algorithmic FLOPs of the tower on these clips (2MNK per GEMM, 4 L^2 D per attention sequence)."""
+    from video_r2_b200.shard import slice_cost
+    return float(sum(t * slice_cost(h, w) for t, h, w in grid))
+
+
+def grid_tokens(grid) -> int:
+    return sum(t * h * w for t, h, w in grid) // 4
+
+
 def workload_desc(world: int) -> str:
     tokens = world * CLIP[0] * CLIP[1] * CLIP[2] // 4
     return (f"Video-R2 eval setting x{world}: {world} clip(s) of 32 frames 448x448 (grid_thw [16,32,32] each, "
@@ -106,7 +128,7 @@ class ClockSampler(threading.Thread):
 # ---------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the HF module Video-R2 executes, on the host cores
 # ---------------------------------------------------------------------------------------------
-def build_hf_reference():
+def build_hf_reference(attn="sdpa", device="cpu", dtype=None):
     import torch
     from transformers.models.qwen2_5_vl.configuration_qwen2_5_vl import Qwen2_5_VLVisionConfig
     from transformers.models.qwen2_5_vl.modeling_qwen2_5_vl import Qwen2_5_VisionTransformerPretrainedModel as V
@@ -115,14 +137,17 @@ def build_hf_reference():
                                  out_hidden_size=3584, patch_size=14, spatial_merge_size=2, temporal_patch_size=2,
                                  window_size=112, fullatt_block_indexes=[7, 15, 23, 31], tokens_per_second=2,
                                  hidden_act="silu")
-    cfg._attn_implementation = "sdpa"
+    cfg._attn_implementation = attn
     with torch.device("meta"):
         m = V._from_config(cfg)
-    m = m.to_empty(device="cpu")
-    g = torch.Generator().manual_seed(0)
+    m = m.to_empty(device=device)
+    g = torch.Generator(device=device).manual_seed(0)
     for p in m.parameters():
         p.data.normal_(0, 0.02, generator=g)
-    m.rotary_pos_emb.inv_freq = 1.0 / (10000.0 ** (torch.arange(0, 40, 2, dtype=torch.float) / 40))
+    m.rotary_pos_emb.inv_freq = (1.0 / (10000.0 ** (torch.arange(0, 40, 2, dtype=torch.float) / 40))).to(device)
+    if dtype is not None:
+        m = m.to(dtype)
+        m.rotary_pos_emb.inv_freq = m.rotary_pos_emb.inv_freq.float()
     return m.eval()
 
 
@@ -199,10 +224,9 @@ def run_reference(args, rank):
 def synth_state_dict(cfg, device, seed=0):
     """Random-init weights of the named architecture, generated on the device (bf16)."""
     import torch
-    from oracle.tower import TowerConfig, weight_shapes
     g = torch.Generator(device=device).manual_seed(seed)
     sd = {}
-    for name, shape in weight_shapes(TowerConfig(depth=cfg.depth)).items():
+    for name, shape in cfg.weight_shapes().items():
         if name.endswith("norm1.weight") or name.endswith("norm2.weight") or name.endswith("ln_q.weight"):
             t = 1.0 + 0.1 * torch.randn(shape, generator=g, device=device)
         else:
@@ -312,7 +336,7 @@ def run_vr2(args, rank, local_rank, world):
     #      every step's pixels + input_ids are copied from pinned host memory and its embeddings + position ids are
     #      copied back inside the timed region; copies of neighbouring steps overlap the kernels (3 streams).
     #      e2e_sync is the same work with a synchronous .to(device) -> forward -> .cpu() per step.
-    pipe = vr2.HostPipeline(tower, depth=2)
+    pipe = vr2.HostPipeline(tower, depth=2, gather_counts=counts if world > 1 else None)
     out_hosts = [torch.empty((tok_local, cfg.out_hidden_size), dtype=torch.bfloat16).pin_memory() for _ in range(2)]
     pos_hosts = [torch.empty((3, world, len(row)), dtype=torch.int64).pin_memory() for _ in range(2)]
 
@@ -321,8 +345,6 @@ def run_vr2(args, rank, local_rank, world):
         for i in range(steps):
             pipe.submit(pix_host[i % n_rot], my_grid, out_host=out_hosts[i % 2], input_ids_host=ids_host,
                         video_grid_thw=vid_thw, second_per_grid_ts=spg, pos_host=pos_hosts[i % 2])
-            if world > 1:
-                all_gather_ragged(pipe._out[(pipe._n - 1) % pipe.depth], counts)
             if i >= 1:
                 next(res)        # the consumer runs one step behind: step i-1's host buffers are complete here
         pipe.drain()
@@ -404,10 +426,12 @@ def run_vr2(args, rank, local_rank, world):
     if not args.no_precise:
         DESC = {"bf16": "bf16 activations x bf16 weights (HF's bf16 arithmetic)",
                 "f16": "fp16 activations x fp16 copies of the bf16 weights (same MMA work as bf16)",
+                "auto": "f16 + the saturation guard read (D2H of the counter + stream sync) after every forward, split re-run "
+                        "if it tripped: the library's shipped default",
                 "split": "hi+lo bf16 activations x bf16 weights (2x MMA work)"}
         outs, modes = {}, {}
         outs[args.precision] = tower(pix_dev[0], my_grid, out_dtype=torch.float32).clone()
-        for mode in ("bf16", "f16", "split"):
+        for mode in ("bf16", "f16", "auto", "split"):
             if mode == args.precision:
                 continue
             tower.set_precision(mode)
@@ -480,6 +504,90 @@ def run_vr2(args, rank, local_rank, world):
         except Exception as e:  # never let the optional measurement break the contract line
             widening["lm_logprob"] = {"error": repr(e)}
 
+    # ---- the other BASELINE configs (outside the headline's timed region).  N = 1: the whole batch on this GPU.
+    #      N > 1: STRONG-scaled through shard.encode_sharded — every rank holds the same pixels (GRPO's RepeatSampler
+    #      hands all ranks the same prompt, grpo_trainer.py:664-679), encodes its frame-balanced share of the temporal
+    #      slices and one (ragged) all-gather returns the full embeddings to every rank; gather_check: rank 0 encodes the
+    #      first slices of the LAST rank's share alone and compares the gathered rows bit for bit.
+    side = {}
+    if not args.no_side_configs:
+        from video_r2_b200.shard import encode_sharded
+        names = ["cfg3_rollout_8x64f_448", "cfg5_ragged_16_clips"] if world > 1 else list(SIDE_CONFIGS)
+        if world == 1:
+            SIDE_CONFIGS["cfg3_one_clip_per_gpu_64f_448"] = [[32, 32, 32]]
+            names = ["cfg1_16f_448", "cfg3_one_clip_per_gpu_64f_448", "cfg4_128f_336x588", "cfg5_ragged_16_clips"]
+        del pix_dev[1:]
+        torch.cuda.empty_cache()
+        for name in names:
+            g = SIDE_CONFIGS[name]
+            try:
+                n_p = sum(t * h * w for t, h, w in g)
+                gen = torch.Generator(device=dev).manual_seed(1234)      # the same pixels on every rank
+                xs = torch.randn(n_p, cfg.patch_dim, generator=gen, device=dev, dtype=torch.bfloat16)
+                sh = partition_slices(g, world)
+                costs = [s_.cost for s_ in sh]
+
+                def run(i):
+                    return encode_sharded(tower, xs, g) if world > 1 else tower(xs, g)
+
+                k = max(2, min(5, args.steps))
+                for i in range(2):
+                    full = run(i)
+                ms = timed(run, k) / k
+                entry = {"grid_thw": g if len(g) <= 2 else f"{len(g)} clips", "patches": n_p, "tokens": n_p // 4,
+                         "ms": ms, "tokens_per_sec": n_p / 4 / (ms * 1e-3), "steps": k,
+                         "tflops_per_gpu": grid_flops(g) / (ms * 1e-3) / 1e12 / world,
+                         "scaling": "strong" if world > 1 else "single GPU"}
+                if world > 1:
+                    entry["cost_imbalance_max_over_mean"] = max(costs) / (sum(costs) / len(costs))
+                    entry["slices_per_rank"] = [sum(r[0] for r in s_.grid) for s_ in sh]
+                    entry["tokens_per_rank"] = [s_.token_hi - s_.token_lo for s_ in sh]
+                    last = [s_ for s_ in sh if s_.patch_hi > s_.patch_lo][-1]
+                    t0, h0, w0 = last.grid[0]
+                    sub = [[min(4, t0), h0, w0]]
+                    n_sub = sub[0][0] * h0 * w0
+                    ok = True
+                    if rank == 0:
+                        alone = tower(xs[last.patch_lo:last.patch_lo + n_sub], sub)
+                        ok = bool(torch.equal(full[last.token_lo:last.token_lo + n_sub // 4], alone))
+                    entry["gather_check"] = ok
+                    entry["gather_check_what"] = (f"rows {last.token_lo}..{last.token_lo + n_sub // 4} of the gathered tensor (rank "
+                                                  f"{sh.index(last)}'s first {sub[0][0]} slices) == the same slices encoded alone on rank 0, torch.equal")
+                side[name] = entry
+                del xs, full
+            except Exception as e:   # an optional line must not cost the contract line
+                side[name] = {"error": repr(e)}
+            torch.cuda.empty_cache()
+        sat = tower.saturation_count() if args.precision in ("f16", "auto") else 0
+    else:
+        sat = tower.saturation_count() if args.precision in ("f16", "auto") else 0
+
+    # ---- the LIBRARY bar on the same GPU: Hugging Face's own module, bf16, flash-attn 2 and sdpa —
+    #      what a Video-R2 user runs today (cuBLAS GEMMs + FA2 mma.sync kernels + eager elementwise)
+    library_bar = None
+    if world == 1 and not args.no_library_bar:
+        library_bar = {}
+        for impl in ("flash_attention_2", "sdpa"):
+            try:
+                m = build_hf_reference(attn=impl, device=dev, dtype=torch.bfloat16)
+                gthw = torch.tensor([list(CLIP)], device=dev)
+                xs = torch.randn(CLIP[0] * CLIP[1] * CLIP[2], cfg.patch_dim, device=dev, dtype=torch.bfloat16)
+
+                def hf(i):
+                    with torch.no_grad():
+                        return m(xs, grid_thw=gthw)
+
+                for i in range(2):
+                    hf(i)
+                ms = timed(hf, 3) / 3
+                library_bar[impl] = {"ms_per_step": ms, "tokens_per_sec": per_clip / (ms * 1e-3)}
+                del m, xs
+            except Exception as e:
+                library_bar[impl] = {"error": repr(e)[:200]}
+            torch.cuda.empty_cache()
+        library_bar["what"] = ("transformers Qwen2_5_VisionTransformerPretrainedModel in bf16 on the same B200, same clip "
+                               "([16,32,32]), random init, 3 steps after 2 warm-ups")
+
     peaks, peak_src = _peaks()
     gu_ms, gu_n = prof.get("gate_up", (0.0, 0))
     gu_avg = gu_ms / max(1, gu_n)
@@ -495,7 +603,7 @@ def run_vr2(args, rank, local_rank, world):
     launches = tower.launch_count(my_grid) + 2
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "f16": "f16", "split": "bf16x2"}[args.precision],
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "f16": "f16", "split": "bf16x2", "auto": "f16"}[args.precision],
         "data": "synthetic",
         "config": {
             "workload": workload_desc(world),
@@ -503,6 +611,7 @@ def run_vr2(args, rank, local_rank, world):
             "l2": "pixel inputs rotate over 4 buffers (154 MB > 126 MB L2); 1.35 GB of weights and 0.44 GB of "
                   "activations stream through HBM every step",
             "operands": {"bf16": "bf16 GEMM/attention operands", "f16": "fp16 activations x fp16 copies of the bf16 weights",
+                         "auto": "fp16 activations x fp16 copies of the bf16 weights, guard read after every forward",
                          "split": "hi+lo bf16 (split) operands"}[args.precision] + ", fp32 accumulate, fp32 residual stream",
             "precision": args.precision,
             "step_tflops": tokens_total * FLOP_PER_TOKEN / (ms_step * 1e-3) / 1e12 / world,
@@ -532,6 +641,11 @@ def run_vr2(args, rank, local_rank, world):
         line["modes"] = modes
     if widening is not None:
         line["widening"] = widening
+    if side:
+        line["configs"] = side
+    if library_bar is not None:
+        line["library_bar"] = library_bar
+    line["saturation_count"] = sat   # f16 range guard over every forward of this run (0: nothing was clamped)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             kind, run = cpu_reference_runner()
@@ -558,11 +672,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="vr2", choices=["vr2", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--precision", default="f16", choices=["bf16", "f16", "split"],
+    ap.add_argument("--precision", default="f16", choices=["bf16", "f16", "split", "auto"],
                     help="operand precision of the headline numbers (include/vr2.h vr2_precision).  Default f16: the fastest "
                          "mode that meets the north-star bound (max-abs 2e-2 vs the fp32 reference); bf16 (the library "
                          "default, HF's own bf16 arithmetic) and split are measured beside it under `modes`")
     ap.add_argument("--no-precise", action="store_true", help="skip the extra split-precision measurement")
+    ap.add_argument("--no-side-configs", action="store_true", help="skip the BASELINE configs 1/3/4/5 lines under `configs`")
+    ap.add_argument("--no-library-bar", action="store_true", help="skip timing HF bf16 (FA2 / sdpa) on the same GPU")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -27,3 +27,8 @@ def test_own_arm_line():
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 16384 * 1176 and e["d2h_bytes_per_step"] > 4096 * 3584
     assert d["gpu_launches"] > 100 * d["steps"]
     assert "workload" in d["config"] and "sm_mhz" in d["clocks"]
+    assert d["saturation_count"] == 0                       # the f16 headline never clamped an activation
+    side = d["configs"]
+    for name in ("cfg1_16f_448", "cfg3_one_clip_per_gpu_64f_448", "cfg4_128f_336x588", "cfg5_ragged_16_clips"):
+        assert side[name].get("ms", 0) > 0 and side[name]["tokens_per_sec"] > 50_000, (name, side[name])
+    assert "library_bar" in d

@@ -25,9 +25,16 @@ from .rope_index import get_rope_index
 class HostPipeline:
     _SNAPS = 256   # guard snapshots kept (= batches that may be in flight)
 
-    def __init__(self, tower, depth: int = 2, rope_config=None):
+    def __init__(self, tower, depth: int = 2, rope_config=None, gather_counts=None, group=None):
+        """gather_counts (tokens per rank, from shard.partition_slices) turns on the SHARDED mode: every batch's
+        embeddings are all-gathered over `group` right behind the tower (on the compute stream, overlapping the
+        neighbouring batches' copies); `gathered(k)` returns the full [sum(counts), D] device tensor of the batch that
+        was submitted k calls ago, and the host result stays this rank's own block."""
         if depth < 1:
             raise ValueError("depth must be >= 1")
+        self.gather_counts = None if gather_counts is None else [int(c) for c in gather_counts]
+        self.group = group
+        self._full = [None] * depth        # device buffers of the gathered embeddings (sharded mode)
         self.tower = tower
         self.dev = tower.device
         self.depth = depth
@@ -45,7 +52,7 @@ class HostPipeline:
         self._n = 0
         # f16 range guard (tower precision "auto" / "f16"): the counter is snapshotted behind every forward into pinned
         # host memory; results() compares neighbouring snapshots and repeats a clamped batch in the split precision
-        self._guard = tower.precision in ("auto", "f16")
+        self._guard = tower.precision in ("auto", "f16") and gather_counts is None
         self._snap = torch.zeros(self._SNAPS, dtype=torch.int32).pin_memory() if self._guard else None   # ring, one per submit
         self._snap_seen = 0
         if self._guard:
@@ -117,7 +124,14 @@ class HostPipeline:
             patchify(x_dev, patch_size=cfg.patch_size, temporal_patch_size=cfg.temporal_patch_size,
                      merge_size=cfg.spatial_merge_size, out=pix)
             x_dev = pix
-        self.tower.forward(x_dev, plan, out=out_dev, check_guard=False)
+        # sharded mode: a clamped block must be repeated BEFORE it is all-gathered (a rank cannot redo the collective
+        # on its own later), so precision "auto" reads the guard synchronously here; otherwise it is deferred to results()
+        sync_guard = self.gather_counts is not None and self.tower.precision == "auto"
+        self.tower.forward(x_dev, plan, out=out_dev, check_guard=sync_guard)
+        if self.gather_counts is not None:
+            from .shard import all_gather_ragged
+            full = self._buf(self._full, slot, (sum(self.gather_counts), self.tower.cfg.out_hidden_size), odt)
+            all_gather_ragged(out_dev, self.gather_counts, self.group, out=full)
         if self._guard:
             if len(self._pending) >= self._SNAPS:
                 raise RuntimeError(f"HostPipeline: more than {self._SNAPS} batches in flight; consume results()")
@@ -161,6 +175,13 @@ class HostPipeline:
         self.tower.run_split(plan, x.contiguous(), out)
         out_host.copy_(out)
         torch.cuda.current_stream(self.dev).synchronize()
+
+    def gathered(self, ago: int = 0) -> torch.Tensor:
+        """Sharded mode: the all-gathered embeddings (device, valid in the compute stream's order) of the batch
+        submitted `ago` submits before the latest one (ago < depth)."""
+        if self.gather_counts is None or not 0 <= ago < self.depth or self._n - 1 - ago < 0:
+            raise ValueError("gathered(): sharded mode with 0 <= ago < depth and that many batches submitted")
+        return self._full[(self._n - 1 - ago) % self.depth]
 
     def results(self):
         """Yields (embeddings_host, position_ids_host or None) in submission order."""

@@ -78,25 +78,42 @@ def partition_slices(grid_thw: Sequence[Sequence[int]], world: int, merge: int =
     return shares
 
 
-def all_gather_ragged(local: torch.Tensor, counts: Sequence[int], group=None) -> torch.Tensor:
+def all_gather_ragged(local: torch.Tensor, counts: Sequence[int], group=None, out: torch.Tensor = None) -> torch.Tensor:
     """One all-gather of per-rank row blocks of different heights.  local: [counts[rank], D].
-    Returns [sum(counts), D] in rank order (== original token order for partition_slices)."""
+    Returns [sum(counts), D] in rank order (== original token order for partition_slices); `out` may supply it.
+
+    Every rank's block is one contiguous row range of the result, so nothing is padded or re-copied: equal heights go
+    through ncclAllGather, unequal ones through one grouped all-gather-v (torch's NCCL `all_gather` with output views of
+    different sizes issues ncclBroadcast per rank inside one ncclGroup), each landing directly in its rows of the
+    result.  (Gloo, which the CPU tests of the routing use, has no uneven all-gather: max-padded blocks there.)"""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     assert local.shape[0] == counts[rank], (local.shape, counts, rank)
     D = local.shape[1]
-    mx = max(counts)
-    if mx == 0:
-        return local.new_empty((0, D))
-    if all(c == mx for c in counts):
-        out = local.new_empty((world * mx, D))
-        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+    total = sum(counts)
+    if out is None:
+        out = local.new_empty((total, D))
+    assert out.shape == (total, D) and out.dtype == local.dtype and out.is_contiguous()
+    if total == 0:
         return out
+    local = local.contiguous()
+    if all(c == counts[0] for c in counts):
+        dist.all_gather_into_tensor(out, local, group=group)
+        return out
+    offs = [0]
+    for c in counts:
+        offs.append(offs[-1] + c)
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather([out[offs[r]:offs[r + 1]] for r in range(world)], local, group=group)
+        return out
+    mx = max(counts)
     padded = local.new_zeros((mx, D))
     padded[: local.shape[0]] = local
     buf = local.new_empty((world, mx, D))
     dist.all_gather_into_tensor(buf.view(world * mx, D), padded, group=group)
-    return torch.cat([buf[r, : counts[r]] for r in range(world)], dim=0)
+    for r in range(world):
+        out[offs[r]:offs[r + 1]] = buf[r, : counts[r]]
+    return out
 
 
 def encode_sharded(tower, pixels: torch.Tensor, grid_thw, group=None, out_dtype=None, gather: bool = True):

@@ -56,6 +56,26 @@ class VisionConfig:
     def patch_dim(self):
         return self.in_channels * self.temporal_patch_size * self.patch_size * self.patch_size
 
+    def weight_shapes(self) -> dict:
+        """name -> shape of every tensor of the HF vision module's state_dict (modeling_qwen2_5_vl.py:91-146, :207-321),
+        in the order `load_state_dict` accepts them: what `vr2_tower_set_weight` must be fed before finalize."""
+        h, i, oh = self.hidden_size, self.intermediate_size, self.out_hidden_size
+        md = h * self.spatial_merge_size ** 2
+        shapes = {"patch_embed.proj.weight": (h, self.in_channels, self.temporal_patch_size, self.patch_size, self.patch_size)}
+        for l in range(self.depth):
+            p = f"blocks.{l}."
+            shapes.update({
+                p + "norm1.weight": (h,), p + "norm2.weight": (h,),
+                p + "attn.qkv.weight": (3 * h, h), p + "attn.qkv.bias": (3 * h,),
+                p + "attn.proj.weight": (h, h), p + "attn.proj.bias": (h,),
+                p + "mlp.gate_proj.weight": (i, h), p + "mlp.gate_proj.bias": (i,),
+                p + "mlp.up_proj.weight": (i, h), p + "mlp.up_proj.bias": (i,),
+                p + "mlp.down_proj.weight": (h, i), p + "mlp.down_proj.bias": (h,),
+            })
+        shapes.update({"merger.ln_q.weight": (h,), "merger.mlp.0.weight": (md, md), "merger.mlp.0.bias": (md,),
+                       "merger.mlp.2.weight": (oh, md), "merger.mlp.2.bias": (oh,)})
+        return shapes
+
     @property
     def head_dim(self):
         return self.hidden_size // self.num_heads
