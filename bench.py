@@ -283,17 +283,41 @@ def run_vr2(args, rank, local_rank, world):
     out_host = torch.empty((tok_local, cfg.out_hidden_size), dtype=torch.bfloat16).pin_memory()
     pos_host = torch.empty((3, world, len(row)), dtype=torch.int64).pin_memory()
 
+    # N > 1: how the merged embeddings reach every rank.  "symmetric" (default): the merger's last GEMM stores each
+    # row into every rank's buffer over NVLink (shard.SymmetricGather: peer bulk copies + one barrier, no collective);
+    # "nccl": ncclAllGather behind the tower.  Falls back to nccl (and says so) if symmetric memory cannot be set up.
+    sg, gather_how = None, "none (1 GPU)"
+    if world > 1:
+        gather_how = "nccl all-gather behind the tower"
+        if args.gather == "symmetric":
+            try:
+                from video_r2_b200.shard import SymmetricGather
+                cap = max(tokens_total, 0 if args.no_side_configs else max(grid_tokens(g_) for g_ in SIDE_CONFIGS.values()))
+                sg = SymmetricGather(tower, cap, depth=2)
+                gather_how = "fused: peer stores from the merger's last GEMM (symmetric memory) + one barrier"
+            except Exception as e:
+                print(f"[bench] symmetric memory unavailable ({e!r}); using the NCCL all-gather", file=sys.stderr)
+                gather_how += f" (symmetric memory unavailable: {type(e).__name__})"
+
     def step_device(i):
-        local = tower(pix_dev[i % n_rot], my_grid)
-        full = all_gather_ragged(local, counts) if world > 1 else local
+        if sg is not None:
+            full = sg.encode_share(pix_dev[i % n_rot], me, tokens_total)
+            local = full[me.token_lo:me.token_hi]
+        else:
+            local = tower(pix_dev[i % n_rot], my_grid)
+            full = all_gather_ragged(local, counts) if world > 1 else local
         pos, delta = vr2.get_rope_index(ids_dev, None, vid_thw, spg, None)
         return local, full, pos
 
     def step_e2e(i):
         x = pix_host[i % n_rot].to(dev, non_blocking=True)
         ids = ids_host.to(dev, non_blocking=True)
-        local = tower(x, my_grid)
-        full = all_gather_ragged(local, counts) if world > 1 else local
+        if sg is not None:
+            full = sg.encode_share(x, me, tokens_total)
+            local = full[me.token_lo:me.token_hi]
+        else:
+            local = tower(x, my_grid)
+            full = all_gather_ragged(local, counts) if world > 1 else local
         pos, delta = vr2.get_rope_index(ids, None, vid_thw, spg, None)
         out_host.copy_(local, non_blocking=True)
         pos_host.copy_(pos, non_blocking=True)
@@ -336,7 +360,8 @@ def run_vr2(args, rank, local_rank, world):
     #      every step's pixels + input_ids are copied from pinned host memory and its embeddings + position ids are
     #      copied back inside the timed region; copies of neighbouring steps overlap the kernels (3 streams).
     #      e2e_sync is the same work with a synchronous .to(device) -> forward -> .cpu() per step.
-    pipe = vr2.HostPipeline(tower, depth=2, gather_counts=counts if world > 1 else None)
+    pipe = vr2.HostPipeline(tower, depth=2, gather_counts=counts if world > 1 else None, symmetric=sg,
+                            share=me if sg is not None else None)
     out_hosts = [torch.empty((tok_local, cfg.out_hidden_size), dtype=torch.bfloat16).pin_memory() for _ in range(2)]
     pos_hosts = [torch.empty((3, world, len(row)), dtype=torch.int64).pin_memory() for _ in range(2)]
 
@@ -528,6 +553,8 @@ def run_vr2(args, rank, local_rank, world):
                 costs = [s_.cost for s_ in sh]
 
                 def run(i):
+                    if sg is not None:
+                        return sg.encode(xs, g)
                     return encode_sharded(tower, xs, g) if world > 1 else tower(xs, g)
 
                 k = max(2, min(5, args.steps))
@@ -615,6 +642,7 @@ def run_vr2(args, rank, local_rank, world):
                          "split": "hi+lo bf16 (split) operands"}[args.precision] + ", fp32 accumulate, fp32 residual stream",
             "precision": args.precision,
             "step_tflops": tokens_total * FLOP_PER_TOKEN / (ms_step * 1e-3) / 1e12 / world,
+            "gather": gather_how,
         },
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic,
@@ -677,6 +705,8 @@ def main():
                          "mode that meets the north-star bound (max-abs 2e-2 vs the fp32 reference); bf16 (the library "
                          "default, HF's own bf16 arithmetic) and split are measured beside it under `modes`")
     ap.add_argument("--no-precise", action="store_true", help="skip the extra split-precision measurement")
+    ap.add_argument("--gather", default="symmetric", choices=["symmetric", "nccl"],
+                    help="N > 1: fused peer-store gather from the merger's last GEMM (default) or an NCCL all-gather behind the tower")
     ap.add_argument("--no-side-configs", action="store_true", help="skip the BASELINE configs 1/3/4/5 lines under `configs`")
     ap.add_argument("--no-library-bar", action="store_true", help="skip timing HF bf16 (FA2 / sdpa) on the same GPU")
     args = ap.parse_args()

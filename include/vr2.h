@@ -174,6 +174,19 @@ int vr2_tower_forward_scatter(vr2_tower* tower, const vr2_plan* plan, const void
                               void* out_dev, int32_t out_dtype, int64_t ld_out, const int32_t* dest_rows_dev,
                               void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* Same forward for the SHARDED multi-GPU mode: the bf16 result [n_tokens, out_hidden] is stored to
+ * n_out (1..8) buffers at once — outs_host[d] is a device pointer to row 0 of this call's tokens in destination d
+ * (row pitch out_hidden), 16-byte aligned; typically this rank's copy of the gathered embeddings and the peer GPUs'
+ * copies of it, mapped into this process (CUDA IPC / symmetric memory), each already offset by this rank's first
+ * token.  The merger's last GEMM stages every 128 x 256 output tile in shared memory and sends each row to every
+ * destination with one 512-byte bulk copy (cp.async.bulk over NVLink for peer destinations): the all-gather of the
+ * merged embeddings overlaps the GEMM tile by tile and needs no collective behind it — only a barrier across the
+ * ranks before the result is read (the kernel ends with a system-scope fence after its copies complete).
+ * No reference counterpart: Video-R2 encodes the same clip on every rank (grpo_trainer.py:664-679). */
+int vr2_tower_forward_multi(vr2_tower* tower, const vr2_plan* plan, const void* pixels_dev, int32_t pixels_dtype,
+                            void* const* outs_host, int32_t n_out, void* workspace_dev, size_t workspace_bytes,
+                            void* stream);
+
 /* Per-kernel-kind device timing.  vr2_tower_profile(mask) selects kinds (bit k = vr2_kernel_kind k; 0 turns it
  * off) and resets the counters; while selected, vr2_tower_forward brackets every launch of that kind with a
  * cudaEvent pair on the caller's stream.  vr2_tower_profile_read synchronises on those events and returns the

@@ -149,3 +149,27 @@ def test_attention_f16(lens):
     err_bf16 = (ops.attention(qkv32.to(torch.bfloat16), cu, heads).float() - _attn_ref(qkv32.to(torch.bfloat16).float(), cu, heads)).abs().max().item()
     print(f"\nf16 {err:.2e}  bf16 {err_bf16:.2e}")
     assert err < 3e-3 and err * 4 < err_bf16, (err, err_bf16)
+
+
+def test_forward_multi_stores_every_destination():
+    """vr2_tower_forward_multi (the fused all-gather's store): the merger's last GEMM writes each row to every
+    destination buffer with bulk copies; every destination must equal the single-output forward bit for bit, rows
+    outside the call's token range stay untouched."""
+    import video_r2_b200 as vr2
+    from oracle import tower as T
+    cfg_o = T.TowerConfig(depth=2, fullatt_block_indexes=(1,))
+    w = T.make_weights(cfg_o, seed=71)
+    tower = vr2.VisionTower(vr2.VisionConfig(depth=2, fullatt_block_indexes=(1,)), w, device="cuda:0", precision="f16")
+    for grid in ([[2, 8, 12], [1, 4, 6]], [[3, 26, 46]], [[1, 2, 2]]):
+        n = sum(t * h * ww for t, h, ww in grid)
+        x = torch.randn(n, 1176, generator=torch.Generator().manual_seed(72)).to(torch.bfloat16).cuda()
+        want = tower(x, grid)
+        for n_dst in (1, 3, 8):
+            lo = 5
+            bufs = [torch.full((n // 4 + 9, 3584), 7.0, dtype=torch.bfloat16, device="cuda") for _ in range(n_dst)]
+            tower.forward_multi(x, grid, [b[lo:].data_ptr() for b in bufs])
+            torch.cuda.synchronize()
+            for b in bufs:
+                assert torch.equal(b[lo:lo + n // 4], want), (grid, n_dst)
+                assert (b[:lo] == 7).all() and (b[lo + n // 4:] == 7).all()
+    assert tower.saturation_count() == 0

@@ -77,3 +77,56 @@ def test_encode_sharded_gloo(world, grid):
     port = 29600 + world * 7 + len(grid)
     mp.spawn(_worker, args=(world, port, grid, ret), nprocs=world, join=True)
     assert all(ret[r] for r in range(world)), dict(ret)
+
+
+_SYM_SCRIPT = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["VR2_ROOT"])
+import video_r2_b200 as vr2
+from video_r2_b200.shard import SymmetricGather, partition_slices
+from oracle import tower as T
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
+torch.cuda.set_device(dev)
+dist.init_process_group("nccl", device_id=dev)
+cfg_o = T.TowerConfig(depth=2, fullatt_block_indexes=(1,))
+w = T.make_weights(cfg_o, seed=81)
+tower = vr2.VisionTower(vr2.VisionConfig(depth=2, fullatt_block_indexes=(1,)), w, device=dev, precision="f16")
+grid = [[3, 8, 12], [2, 4, 6], [1, 26, 46]]
+n = sum(t * h * ww for t, h, ww in grid)
+x = torch.randn(n, 1176, generator=torch.Generator().manual_seed(82)).to(torch.bfloat16).to(dev)
+sg = SymmetricGather(tower, n // 4 + 100, depth=2)
+outs = [sg.encode(x, grid).clone() for _ in range(3)]        # rotates through both buffers
+whole = tower(x, grid)                                       # the unsharded forward on this rank
+shares = partition_slices(grid, world)
+for o in outs:
+    assert o.shape == whole.shape
+    for s in shares:                                         # each rank's rows == that share encoded alone, bit for bit
+        if s.patch_hi > s.patch_lo:
+            alone = tower(x[s.patch_lo:s.patch_hi], [list(r) for r in s.grid])
+            assert torch.equal(o[s.token_lo:s.token_hi], alone), (rank, s)
+    assert (o.float() - whole.float()).abs().max().item() < 2e-2
+torch.cuda.synchronize()
+dist.barrier()
+if rank == 0:
+    print("SYMMETRIC_GATHER_OK world", world)
+dist.destroy_process_group()
+"""
+
+
+@pytest.mark.gpu
+def test_symmetric_gather_on_the_gpus_present(tmp_path):
+    """shard.SymmetricGather (peer stores from the merger's last GEMM into every rank's symmetric buffer + one barrier)
+    with as many ranks as the box has GPUs (1 on the driver's test box: the symmetric-memory rendezvous, the
+    multi-destination store and the barrier all still run; 2/4/8 under `gpurun --gpus N`)."""
+    import subprocess
+    import sys
+    import torch
+    n = min(torch.cuda.device_count(), 8)
+    script = tmp_path / "sym.py"
+    script.write_text(_SYM_SCRIPT)
+    env = dict(os.environ, VR2_ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", "29577", str(script)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0 and "SYMMETRIC_GATHER_OK" in out.stdout, (out.stdout[-1500:], out.stderr[-3000:])

@@ -83,6 +83,7 @@ SIGNATURES = {
     "vr2_tower_get_precision": (C.c_int32, [_P]),
     "vr2_tower_workspace_bytes": (C.c_size_t, [_P, C.c_int64]),
     "vr2_tower_forward": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int32, _P, C.c_size_t, _P]),
+    "vr2_tower_forward_multi": (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(C.c_void_p), C.c_int32, _P, C.c_size_t, _P]),
     "vr2_tower_forward_scatter": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int32, C.c_int64, _P, _P, C.c_size_t, _P]),
     "vr2_token_positions_scratch_bytes": (C.c_size_t, [C.c_int64]),
     "vr2_token_positions": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int64, _P, C.POINTER(C.c_int64), _P]),

@@ -99,9 +99,6 @@ __device__ __forceinline__ float ex2_approx(float x) {   // MUFU.EX2: 2 ulp, exa
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void named_bar_sync(int id, int threads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
-}
 
 constexpr int kThreads = 320;   // 2 softmax warpgroups (one per stream) + producer warp + MMA warp
 

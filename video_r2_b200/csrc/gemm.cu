@@ -64,6 +64,25 @@ struct Cfg {
 
 constexpr int kStageBytes = 2048;  // per epilogue warp
 
+// EPI_STORE_MULTI (the merger's last GEMM in the sharded multi-GPU mode): the bf16 tile is staged whole in shared
+// memory — [128 rows][256 columns] with 528-byte rows (512 + 16: thread-per-row 16-byte stores hit every bank once) —
+// and every row leaves as ONE 512-byte bulk copy per destination buffer.  The destinations are the same rows of
+// `n_multi` buffers, the local result and the peers' (NVLink-mapped) copies of it: the all-gather of the merged
+// embeddings happens tile by tile inside the GEMM that produces them instead of as a collective behind it.
+// The ring gives up one stage for the 66 KB tile.
+constexpr int kMultiRowBytes = 528;
+constexpr int kMultiTileBytes = BM * kMultiRowBytes;
+
+template <int BN, int EPI, bool SPLIT>
+__host__ __device__ constexpr int stages_of() {
+  return EPI == EPI_STORE_MULTI ? 3 : Cfg<BN, SPLIT>::stages;
+}
+template <int BN, int EPI, bool SPLIT>
+__host__ __device__ constexpr int smem_of() {
+  using C = Cfg<BN, SPLIT>;
+  return EPI == EPI_STORE_MULTI ? 3 * C::stage_bytes + C::bar_bytes + kMultiTileBytes + 1024 : C::smem_bytes;
+}
+
 // Per-warp staging tile that turns thread-per-row register data into row-contiguous global
 // accesses.  Two views of the same 2 KB: fp32 [32 rows][16] (64-byte rows, 4 x 16-byte chunks,
 // chunk index XOR-swizzled by (row >> 1) & 3 so both the row-per-thread and the 8-rows-per-
@@ -180,17 +199,18 @@ __global__ void __launch_bounds__(Cfg<BN, SPLIT>::threads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
             const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
   using C = Cfg<BN, SPLIT>;
+  constexpr int kStages = stages_of<BN, EPI, SPLIT>();
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment in the shared window.
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::stages * C::stage_bytes);
-  uint64_t* empty_bar = full_bar + C::stages;
-  uint64_t* acc_full = empty_bar + C::stages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * C::stage_bytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* acc_full = empty_bar + kStages;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  uint8_t* stage_base = smem + C::stages * C::stage_bytes + C::bar_bytes;
+  uint8_t* stage_base = smem + kStages * C::stage_bytes + C::bar_bytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -207,7 +227,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     tma_prefetch_desc(&tmA);
     if constexpr (SPLIT) tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < C::stages; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
@@ -233,8 +253,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int m0 = (tile / num_n_blocks) * BM;
       const int n0 = (tile % num_n_blocks) * BN;
       for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
-        const uint32_t s = it % C::stages;
-        const uint32_t ph = (it / C::stages) & 1u;
+        const uint32_t s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1u;
         mbar_wait(&empty_bar[s], ph ^ 1u);
         uint8_t* sa = smem + s * C::stage_bytes;
         uint8_t* sb = sa + C::a_bytes;
@@ -259,8 +279,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + as * kAccStride;
       for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
-        const uint32_t s = it % C::stages;
-        const uint32_t ph = (it / C::stages) & 1u;
+        const uint32_t s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1u;
         mbar_wait(&full_bar[s], ph);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * C::stage_bytes);
@@ -313,7 +333,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const bool valid = r < p.M;
       const int rows_valid = min(32, max(0, p.M - row0));
 
-      if constexpr (EPI == EPI_STORE) {
+      if constexpr (EPI == EPI_STORE_MULTI) {
+        // thread = row: its GC columns -> the staged tile; the quarter's four column-group warps meet on a named
+        // barrier, then the cg == 0 warp sends each of its 32 rows to every destination with one bulk copy
+        static_assert(BN == 256, "the multi-destination store stages a 128 x 256 tile");
+        const int64_t dest = valid ? (p.row_map != nullptr ? p.row_map[r] : r) : -1;
+        uint8_t* srow = stage_base + (quarter * 32 + lane) * kMultiRowBytes;
+        if (cg == 0) tma_store_wait_read<0>();                   // the previous tile's copies have read this row
+        named_bar_sync(1 + quarter, 128);                        // ... and the other column groups may overwrite it
+#pragma unroll 1
+        for (int c = cg * GC; c < (cg + 1) * GC; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c, v);
+          tmem_ld_wait();
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias != nullptr && n0 + c + j < p.N) b = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + j));
+            pk[j / 2] = pack_bf16x2(__uint_as_float(v[j]) + b.x, __uint_as_float(v[j + 1]) + b.y);
+            pk[j / 2 + 1] = pack_bf16x2(__uint_as_float(v[j + 2]) + b.z, __uint_as_float(v[j + 3]) + b.w);
+          }
+          *reinterpret_cast<uint4*>(srow + c * 2) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(srow + c * 2 + 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        fence_proxy_async();                                     // this thread's staged columns -> visible to the bulk copies
+        named_bar_sync(1 + quarter, 128);
+        if (cg == 0 && dest >= 0) {
+          const int cols = min(BN, p.N - n0);                    // N % 8 == 0: a multiple of 16 bytes
+          for (int d = 0; d < p.n_multi; ++d) {
+            __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.multi_out[d]) + dest * p.ld_out + n0;
+            bulk_store(o, srow, static_cast<uint32_t>(cols) * 2u);
+          }
+        }
+        if (cg == 0) tma_store_commit();
+      } else if constexpr (EPI == EPI_STORE) {
         const bool direct = p.row_map != nullptr;   // scattered rows (inverse window permute): row-per-thread stores
         const int64_t dest = valid ? (direct ? p.row_map[r] : r) : 0;
         const bool store_row = valid && dest >= 0;   // a negative destination = "no place for this token" (scatter)
@@ -596,6 +650,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
     }
+    if constexpr (EPI == EPI_STORE_MULTI) {
+      // every bulk copy of this thread has been written (not only read from shared memory), and the writes — some of
+      // them into peer GPUs' memory — are ordered before whatever signals the peers after this kernel
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+      __threadfence_system();
+    }
   }
 
   tc_fence_before();
@@ -633,13 +693,13 @@ cudaError_t launch(const GemmArgs& a, int num_sms, cudaStream_t stream, const ch
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, EPI, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         C::smem_bytes);
+                                         smem_of<BN, EPI, SPLIT>());
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
   const int tiles = ((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  gemm_kernel<BN, EPI, SPLIT><<<grid, C::threads, C::smem_bytes, stream>>>(tmA, tmA2, tmB, a);
+  gemm_kernel<BN, EPI, SPLIT><<<grid, C::threads, smem_of<BN, EPI, SPLIT>(), stream>>>(tmA, tmA2, tmB, a);
   return cudaGetLastError();
 }
 
@@ -730,6 +790,18 @@ cudaError_t gemm_launch(const GemmArgs& a, int num_sms, cudaStream_t stream, con
     }
   }
   switch (a.epilogue) {
+    case EPI_STORE_MULTI:
+      if (a.n_multi < 1 || a.n_multi > kMaxMultiOut || a.A_lo != nullptr || (a.flags & (GEMM_OUT_F32 | GEMM_OUT_F16 | GEMM_GELU)) ||
+          a.N % 8 != 0 || (a.ld_out * 2) % 16 != 0) {
+        *err = "gemm: EPI_STORE_MULTI takes 1..8 bf16 destinations, N % 8 == 0, no split operand / GELU / fp32 output";
+        return cudaErrorInvalidValue;
+      }
+      for (int d = 0; d < a.n_multi; ++d)
+        if (a.multi_out[d] == nullptr || (reinterpret_cast<uintptr_t>(a.multi_out[d]) & 15)) {
+          *err = "gemm: EPI_STORE_MULTI destinations must be non-null and 16-byte aligned";
+          return cudaErrorInvalidValue;
+        }
+      return launch<256, EPI_STORE_MULTI, false>(a, num_sms, stream, err);
     case EPI_STORE:
       if ((a.flags & GEMM_OUT_F32) ? a.out_f32 == nullptr : a.out_bf16 == nullptr) {
         *err = "gemm: missing output";

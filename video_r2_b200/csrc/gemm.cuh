@@ -15,7 +15,11 @@ enum GemmEpilogue : int {
   EPI_QKV = 2,     // v = acc*rstd + bias; 2-D rotary on q,k heads; bf16 [M,3840]
   EPI_SWIGLU = 3,  // h = silu(g*rstd+bg) * (u*rstd+bu), gate/up interleaved per 256-column tile
   EPI_LOGPROB = 4, // LM head without logits: per (row, 256-column block) max / sum-exp of acc * inv_temp, target logit
+  EPI_STORE_MULTI = 5,  // out = acc + bias as bf16, each (row-mapped) row written to n_multi destination buffers
+                        // (local + peer GPUs' copies of the result: the all-gather fused into the producing GEMM)
 };
+
+constexpr int kMaxMultiOut = 8;
 
 enum GemmFlags : int {
   GEMM_ADD_RESID = 1,  // EPI_RESID: read-modify-write x
@@ -65,6 +69,9 @@ struct GemmArgs {
   // saturate, so the element-wise scan only runs for rows that might)
   unsigned int* sat;
   float sat_wmax2;
+  // EPI_STORE_MULTI: destination buffers (row pitch ld_out each), device or peer-mapped device memory
+  void* multi_out[kMaxMultiOut];
+  int n_multi;
   const int32_t* pos_win;  // [M] hpos | wpos << 16
   const float* pos_tab;    // [n_pos, 40]
   int n_pos;

@@ -226,6 +226,17 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* src, 
                : "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(src)), "r"(c0), "r"(c1)
                : "memory");
 }
+// 1-D bulk copy shared -> global (any global address of the unified space, peer-mapped memory included); 16-byte
+// aligned on both sides, size a multiple of 16; joins the thread's current bulk group
+__device__ __forceinline__ void bulk_store(void* dst_global, const void* src_smem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+               :
+               : "l"(reinterpret_cast<uint64_t>(dst_global)), "r"(smem_u32(src_smem)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // Waits until at most N of this thread's bulk groups still READ their shared-memory source.
 template <int N>

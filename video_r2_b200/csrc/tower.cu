@@ -415,9 +415,10 @@ cudaError_t compose_map(const int32_t* out_map, const int32_t* dest_rows, int32_
 
 // dest_rows == nullptr: merged token k -> out[k, :] (row pitch out_hidden).  Otherwise token k -> out[dest_rows[k], :]
 // with row pitch ld_out: the masked_scatter of the caller fused into the merger's last store.
+// multi != nullptr: the result (bf16) is stored to the n_multi buffers multi[0..] instead of `out` (vr2_tower_forward_multi).
 static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pixels, int32_t pixels_dtype, void* out,
                               int32_t out_dtype, const int32_t* dest_rows, int64_t ld_out, void* workspace,
-                              size_t workspace_bytes, void* stream_v) {
+                              size_t workspace_bytes, void* stream_v, void* const* multi = nullptr, int n_multi = 0) {
   if (t == nullptr || plan == nullptr || pixels == nullptr || out == nullptr || workspace == nullptr)
     return fail(VR2_ERR_ARG, "vr2_tower_forward: null argument");
   if (!t->finalized) return fail(VR2_ERR_STATE, "vr2_tower_forward: weights not finalized");
@@ -564,6 +565,13 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
     a.out_bf16 = static_cast<__nv_bfloat16*>(out); a.out_f32 = static_cast<float*>(out);
     a.ld_out = t->cfg.out_hidden_size;
     a.row_map = plan->out_map;  // inverse window permute fused into the store (HF :512-513)
+    if (multi != nullptr) {
+      // sharded multi-GPU mode: every row goes to all destinations (this rank's and the peers' copies of the result)
+      a.epilogue = EPI_STORE_MULTI;
+      a.flags = act_in;
+      a.n_multi = n_multi;
+      for (int d = 0; d < n_multi; ++d) a.multi_out[d] = multi[d];
+    }
     if (dest_rows != nullptr) {
       VR2_CUDA(compose_map(plan->out_map, dest_rows, w.cmap, T, s));
       a.row_map = w.cmap;
@@ -578,6 +586,18 @@ extern "C" int vr2_tower_forward(vr2_tower* t, const vr2_plan* plan, const void*
                                  void* out, int32_t out_dtype, void* workspace, size_t workspace_bytes,
                                  void* stream_v) {
   return tower_forward_impl(t, plan, pixels, pixels_dtype, out, out_dtype, nullptr, 0, workspace, workspace_bytes, stream_v);
+}
+
+extern "C" int vr2_tower_forward_multi(vr2_tower* t, const vr2_plan* plan, const void* pixels, int32_t pixels_dtype,
+                                       void* const* outs, int32_t n_out, void* workspace, size_t workspace_bytes,
+                                       void* stream_v) {
+  if (outs == nullptr || n_out < 1 || n_out > kMaxMultiOut)
+    return fail(VR2_ERR_ARG, "vr2_tower_forward_multi: 1..%d destinations", kMaxMultiOut);
+  for (int d = 0; d < n_out; ++d)
+    if (outs[d] == nullptr || (reinterpret_cast<uintptr_t>(outs[d]) & 15))
+      return fail(VR2_ERR_ARG, "vr2_tower_forward_multi: destination %d is null or not 16-byte aligned", d);
+  return tower_forward_impl(t, plan, pixels, pixels_dtype, outs[0], VR2_BF16, nullptr, 0, workspace, workspace_bytes, stream_v,
+                            outs, n_out);
 }
 
 extern "C" int vr2_tower_forward_scatter(vr2_tower* t, const vr2_plan* plan, const void* pixels, int32_t pixels_dtype,

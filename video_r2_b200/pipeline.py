@@ -25,7 +25,8 @@ from .rope_index import get_rope_index
 class HostPipeline:
     _SNAPS = 256   # guard snapshots kept (= batches that may be in flight)
 
-    def __init__(self, tower, depth: int = 2, rope_config=None, gather_counts=None, group=None):
+    def __init__(self, tower, depth: int = 2, rope_config=None, gather_counts=None, group=None, symmetric=None,
+                 share=None):
         """gather_counts (tokens per rank, from shard.partition_slices) turns on the SHARDED mode: every batch's
         embeddings are all-gathered over `group` right behind the tower (on the compute stream, overlapping the
         neighbouring batches' copies); `gathered(k)` returns the full [sum(counts), D] device tensor of the batch that
@@ -34,6 +35,11 @@ class HostPipeline:
             raise ValueError("depth must be >= 1")
         self.gather_counts = None if gather_counts is None else [int(c) for c in gather_counts]
         self.group = group
+        # symmetric: a shard.SymmetricGather + this rank's RankShare -> the gather is fused into the tower's last GEMM
+        # (peer stores + one barrier) instead of an NCCL all-gather behind it
+        self.symmetric, self.share = symmetric, share
+        if symmetric is not None and (share is None or gather_counts is None or symmetric.depth < depth):
+            raise ValueError("HostPipeline(symmetric=...) needs share=, gather_counts= and symmetric.depth >= depth")
         self._full = [None] * depth        # device buffers of the gathered embeddings (sharded mode)
         self.tower = tower
         self.dev = tower.device
@@ -127,8 +133,13 @@ class HostPipeline:
         # sharded mode: a clamped block must be repeated BEFORE it is all-gathered (a rank cannot redo the collective
         # on its own later), so precision "auto" reads the guard synchronously here; otherwise it is deferred to results()
         sync_guard = self.gather_counts is not None and self.tower.precision == "auto"
-        self.tower.forward(x_dev, plan, out=out_dev, check_guard=sync_guard)
-        if self.gather_counts is not None:
+        if self.symmetric is not None:
+            full = self.symmetric.encode_share(x_dev, self.share, sum(self.gather_counts), check_guard=sync_guard)
+            self._full[slot] = full
+            out_dev = full[self.share.token_lo:self.share.token_hi]
+        else:
+            self.tower.forward(x_dev, plan, out=out_dev, check_guard=sync_guard)
+        if self.gather_counts is not None and self.symmetric is None:
             from .shard import all_gather_ragged
             full = self._buf(self._full, slot, (sum(self.gather_counts), self.tower.cfg.out_hidden_size), odt)
             all_gather_ragged(out_dev, self.gather_counts, self.group, out=full)

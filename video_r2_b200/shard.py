@@ -116,6 +116,70 @@ def all_gather_ragged(local: torch.Tensor, counts: Sequence[int], group=None, ou
     return out
 
 
+class SymmetricGather:
+    """The all-gather of the sharded mode WITHOUT a collective: every rank owns `depth` buffers [capacity, D] bf16 in
+    symmetric memory (torch.distributed._symmetric_memory: the same allocation on every GPU of the node, each mapped
+    into every process over NVLink), and the merger's last GEMM of rank r stores its token rows straight into rows
+    [token_lo_r, token_hi_r) of EVERY rank's buffer (`VisionTower.forward_multi`).  What is left of the collective is
+    one barrier across the ranks after the tower (signal pads in the same symmetric allocation, enqueued on the
+    compute stream; no host synchronisation).
+
+    Buffers rotate (depth >= 2): the tensor returned by `encode` stays valid until `depth - 1` further calls have been
+    made, for consumers enqueued on the same stream.  One barrier per call is enough: rank r starts writing buffer
+    n % depth in call n only after it has passed the barrier of call n - 1, which every rank reaches — in stream order —
+    only after its reads of call n - depth's result (the previous tenant of that buffer) have completed."""
+
+    def __init__(self, tower, capacity_tokens: int, group=None, depth: int = 2):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.tower = tower
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        if self.world > 8:
+            raise ValueError("SymmetricGather: at most 8 ranks (one NVLink node)")
+        if depth < 2:
+            raise ValueError("SymmetricGather: depth >= 2 (the barrier of call n - 1 protects buffer n % depth)")
+        self.D = tower.cfg.out_hidden_size
+        self.capacity = int(capacity_tokens)
+        self.depth = depth
+        self._bufs, self._hdls = [], []
+        with torch.cuda.device(tower.device):
+            for _ in range(depth):
+                t = symm_mem.empty((self.capacity, self.D), dtype=torch.bfloat16, device=tower.device)
+                h = symm_mem.rendezvous(t, self.group)
+                self._bufs.append(t)
+                self._hdls.append(h)
+        self._n = 0
+
+    def encode(self, pixels: torch.Tensor, grid_thw) -> torch.Tensor:
+        """Every rank holds the same `pixels` [N, 1176] / `grid_thw` (GRPO: RepeatSampler hands every rank the same
+        prompt).  Returns the full [N/4, D] embeddings (a view of this rank's symmetric buffer), valid in the current
+        stream's order."""
+        if isinstance(grid_thw, torch.Tensor):
+            grid = grid_thw.detach().to("cpu").reshape(-1, 3).tolist()
+        else:
+            grid = [list(map(int, r)) for r in grid_thw]
+        shares = partition_slices(grid, self.world, self.tower.cfg.spatial_merge_size)
+        me = shares[self.rank]
+        return self.encode_share(pixels[me.patch_lo:me.patch_hi], me, shares[-1].token_hi)
+
+    def encode_share(self, local_pixels: torch.Tensor, share: RankShare, total_tokens: int, check_guard=None) -> torch.Tensor:
+        """This rank's part only: `local_pixels` are the rows of `share` (its clips cut at slice boundaries); the
+        result rows [share.token_lo, share.token_hi) are written into every rank's buffer, the rest arrives from the
+        peers.  Every rank of the group must make the matching call."""
+        if total_tokens > self.capacity:
+            raise ValueError(f"SymmetricGather: {total_tokens} tokens exceed the capacity {self.capacity}")
+        slot = self._n % self.depth
+        self._n += 1
+        hdl, buf = self._hdls[slot], self._bufs[slot]
+        if share.patch_hi > share.patch_lo:
+            row_bytes = self.D * 2
+            dests = [int(hdl.buffer_ptrs[r]) + share.token_lo * row_bytes for r in range(self.world)]
+            self.tower.forward_multi(local_pixels, [list(r) for r in share.grid], dests, check_guard=check_guard)
+        hdl.barrier(channel=0)      # every rank's rows have landed everywhere
+        return buf[:total_tokens]
+
+
 def encode_sharded(tower, pixels: torch.Tensor, grid_thw, group=None, out_dtype=None, gather: bool = True):
     """Every rank holds the same `pixels` [N,1176] / `grid_thw`; rank r encodes its slice range and the
     merged embeddings are all-gathered.  Returns [N/4, out_hidden] on every rank (or the local block

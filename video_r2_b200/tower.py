@@ -331,7 +331,12 @@ class VisionTower:
         base = ws.data_ptr()
         aligned = (base + 1023) & ~1023
         with torch.cuda.device(self.device):
-            if rows is None:
+            if isinstance(out, (list, tuple)):      # forward_multi: raw destination pointers
+                ptrs = (C.c_void_p * len(out))(*[int(v) for v in out])
+                check(lib().vr2_tower_forward_multi(self._h, plan._h, x.data_ptr(), _dtype_code(x.dtype), ptrs, len(out),
+                                                    aligned, ws.numel() - (aligned - base), _stream_ptr(self.device)),
+                      "vr2_tower_forward_multi")
+            elif rows is None:
                 check(lib().vr2_tower_forward(self._h, plan._h, x.data_ptr(), _dtype_code(x.dtype), out.data_ptr(),
                                               _dtype_code(out.dtype), aligned, ws.numel() - (aligned - base),
                                               _stream_ptr(self.device)), "vr2_tower_forward")
@@ -388,6 +393,26 @@ class VisionTower:
             raise ValueError(f"dest_rows has {rows.numel()} entries for {plan.num_tokens} visual tokens")
         self._launch(plan, x, dest, rows)
         return dest
+
+    @torch.no_grad()
+    def forward_multi(self, hidden_states: torch.Tensor, grid_thw, dest_ptrs, check_guard=None):
+        """Tower forward whose bf16 result [n_tokens, out_hidden] is stored to every buffer of `dest_ptrs` at once
+        (ints: device addresses of row 0 of this call's tokens in each destination, local or peer-mapped memory; at
+        most 8) — the all-gather of the sharded multi-GPU mode fused into the merger's last GEMM
+        (include/vr2.h vr2_tower_forward_multi).  The caller owns the cross-rank barrier that must follow."""
+        plan = self.plan(grid_thw)
+        x = hidden_states
+        if x.device != self.device:
+            x = x.to(self.device, non_blocking=True)
+        if x.dtype not in (torch.float32, torch.bfloat16):
+            x = x.to(torch.bfloat16)
+        x = x.contiguous()
+        if x.dim() != 2 or x.shape[1] != self.cfg.patch_dim or x.shape[0] != plan.num_patches:
+            raise ValueError(f"hidden_states must be [{plan.num_patches}, {self.cfg.patch_dim}], got {tuple(x.shape)}")
+        dest_ptrs = [int(p) for p in dest_ptrs]
+        if not 1 <= len(dest_ptrs) <= 8:
+            raise ValueError("forward_multi takes 1..8 destinations")
+        self._launch(plan, x, dest_ptrs, None, check_guard)
 
     KERNEL_KINDS = ("cast", "patch_embed", "qkv", "attn_window", "attn_full", "proj", "gate_up", "down",
                     "merger_norm", "fc1", "fc2")
