@@ -14,12 +14,14 @@
 //   warp 8             TMA producer: Q per item, K|V blocks of both streams into one 3-stage ring, in the fixed
 //                      (stream, block) order the MMA issuer consumes them.  A 128 x 80 operand tile is two boxes:
 //                      64 columns (128-byte swizzle) + 16 columns (32-byte swizzle).
-//   warp 9             tcgen05.mma issuer:  S = Q K_j^T (5 MMAs of 128x128x16),  O_j = P_j V_j (8 k-steps x
-//                      {N=64, N=16}, V as an MN-major operand, fresh accumulator per block)
+//   warp 9             tcgen05.mma issuer:  S = Q K_j^T (5 MMAs of 128x128x16),  O += P_j V_j (8 k-steps x
+//                      {N=64, N=16}, V as an MN-major operand; O accumulates in TMEM over the blocks of an item)
 //   warps 4x..4x+3     softmax of stream x, thread = query row = TMEM lane: row max, exp2, P_j -> shared memory
-//                      (bf16, the K-major 128B-swizzled layout the MMA reads), running max / sum; the block outputs
-//                      O_j are folded into 80 fp32 registers per row with the usual rescale.  Result -> shared
-//                      memory (aliasing the stream's P buffer) -> one TMA store.
+//                      (bf16, the K-major 128B-swizzled layout the MMA reads), running sum.  The exponentials are taken
+//                      against a reference maximum that is raised lazily (only when a block's maximum exceeds it by
+//                      2^8 in the exponent), and only then is O rescaled — in TMEM, by these warps (tcgen05.ld / st)
+//                      between two P V batches.  After the last block O -> registers -> normalised -> shared memory
+//                      (aliasing the stream's P buffer) -> one TMA store.
 // fp32 scores, softmax and accumulation; bf16 operands (P is rounded to bf16 like q, k, v).
 #include "attention.cuh"
 
@@ -245,8 +247,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
         __syncwarp();
         ++nblk_done[x];
       };
-      auto issue_pv = [&](int x) {            // O_x = P_x V for the stream's current block
-        mbar_wait(&p_ready[x], npv_done[x] & 1u);   // P is in shared memory, the previous O has been folded
+      auto issue_pv = [&](int x, bool first) {   // O_x (+)= P_x V for the stream's current block (first: of the item)
+        mbar_wait(&p_ready[x], npv_done[x] & 1u);   // P is in shared memory (and O rescaled if the reference maximum moved)
         tc_fence_after();
         ++npv_done[x];
         const uint32_t s = stage_of[x];
@@ -257,8 +259,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
 #pragma unroll
           for (int kk = 0; kk < TK / 16; ++kk) {
             const uint64_t da = umma_desc_sw128(p_addr + (kk >> 2) * (TQ * 128) + (kk & 3) * 32);
-            umma_bf16(d, da, desc_mn_sw128(v_addr + kk * 2048), id_o64, kk != 0 ? 1u : 0u);
-            umma_bf16(d + 64, da, desc_mn_sw32(v_addr + Q64_BYTES + kk * 512), id_o16, kk != 0 ? 1u : 0u);
+            umma_bf16(d, da, desc_mn_sw128(v_addr + kk * 2048), id_o64, (kk != 0 || !first) ? 1u : 0u);
+            umma_bf16(d + 64, da, desc_mn_sw32(v_addr + Q64_BYTES + kk * 512), id_o16, (kk != 0 || !first) ? 1u : 0u);
           }
           umma_commit(&kv_empty[s]);        // K (read by S earlier) and V of this block are free once these retire
           umma_commit(&o_full[x]);
@@ -279,7 +281,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
         for (int j = 0; j < nmax; ++j)
           for (int x = 0; x < 2; ++x)
             if (j < nb[x]) {
-              issue_pv(x);
+              issue_pv(x, j == 0);
               if (j + 1 < nb[x]) issue_s(x, j + 2 == nb[x]);
             }
       }
@@ -305,23 +307,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
         lo = sg.x;
         hi = sg.y;
       }
-      float o[HD];
-#pragma unroll
-      for (int i = 0; i < HD; ++i) o[i] = 0.f;
-      float m_run = -INFINITY, l_run = 0.f, corr_prev = 1.f;
-
-      auto fold = [&](uint32_t b, float corr) {   // o = o * corr + O of block b (single O buffer per stream)
-        mbar_wait(&o_full[x], b & 1u);
-        tc_fence_after();
-        uint32_t v[HD];
-        tmem_ld32(to, v);
-        tmem_ld32(to + 32, v + 32);
-        tmem_ld16(to + 64, v + 64);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < HD; ++i) o[i] = fmaf(o[i], corr, __uint_as_float(v[i]));
-        tc_fence_before();
-      };
+      // O accumulates in TMEM across the key blocks of the item (the P V MMAs of block j > 0 accumulate).  The
+      // exponentials of a row are taken against m_ref, which follows the running maximum LAZILY: it moves — and O and
+      // the running sum are rescaled, O in TMEM — only when a block's maximum exceeds it by more than kTau in the
+      // exponent (P then stays <= 2^kTau, far inside bf16 / fp16 range, sums and O are fp32).  After the first block
+      // or two the maximum rarely grows that much, so the per-block cost is the softmax itself, not an 80-column
+      // read-modify-write of O.
+      constexpr float kTau = 8.0f;
+      float m_ref = -INFINITY, l_run = 0.f;
 
       // the previous item's TMA store has read the staging area that aliases this stream's P buffer
       if (tid == 0) tma_store_wait_read<0>();
@@ -365,11 +358,33 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
             }
           }
         }
-        const float m_new = fmaxf(m_run, mx);
-        // exp2((s - m) * scale): scores stay unscaled in TMEM, the 1/sqrt(d) * log2(e) factor is applied here
-        const float m_scaled = m_new == -INFINITY ? 0.f : m_new * scale_log2;
-        const float corr = m_run == -INFINITY ? 0.f : ex2_approx(m_run * scale_log2 - m_scaled);
-        m_run = m_new;
+        if (j == 0) {
+          m_ref = mx;
+        } else {
+          // S_j complete => the P V of block j - 1 (issued before it) has retired: O holds blocks 0 .. j-1 and may be
+          // rescaled; observing o_full here also keeps this thread in step with the barrier's phases
+          mbar_wait(&o_full[x], (b - 1) & 1u);
+          const bool need = (mx - m_ref) * scale_log2 > kTau || (m_ref == -INFINITY && mx != -INFINITY);
+          if (__any_sync(0xffffffffu, need)) {          // tcgen05.ld / st are warp-collective
+            tc_fence_after();
+            const float m_new = fmaxf(m_ref, mx);
+            const float f = m_ref == -INFINITY ? 0.f : ex2_approx((m_ref - m_new) * scale_log2);
+#pragma unroll 1
+            for (int c = 0; c < HD; c += 16) {       // rare path
+              uint32_t v[16];
+              tmem_ld16(to + c, v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+              tmem_st16(to + c, v);
+            }
+            tmem_st_wait();
+            l_run *= f;
+            m_ref = m_new;
+          }
+        }
+        // exp2((s - m_ref) * scale): scores stay unscaled in TMEM, the 1/sqrt(d) * log2(e) factor is applied here
+        const float m_scaled = m_ref == -INFINITY ? 0.f : m_ref * scale_log2;
         // pass 2: probabilities -> bf16 -> shared memory in the K-major SWIZZLE_128B layout the P V MMAs read
         uint8_t* prow = pbuf + tid * 128;
         float rs0 = 0.f, rs1 = 0.f;
@@ -416,17 +431,26 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
             *reinterpret_cast<uint4*>(atom + (((ch0 + q) ^ (tid & 7)) << 4)) =
                 make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         }
-        l_run = l_run * corr + (rs0 + rs1);
-        tc_fence_before();       // this thread's TMEM reads of S are complete (tcgen05.wait::ld above)
-        // fold the previous block's output BEFORE releasing P: the stream has one O buffer and the P V that
-        // p_ready allows overwrites it
-        if (j > 0) fold(b - 1, corr_prev);
-        corr_prev = corr;
+        l_run += rs0 + rs1;
+        tc_fence_before();       // this thread's TMEM reads of S (and writes of O) are complete
         fence_proxy_async();     // P visible to the tensor core's shared-memory reads
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_ready[x]);
       }
-      fold(nblk_done + nblk - 1, corr_prev);
+      // the item's last P V has retired: O (80 fp32 columns of this row) -> registers
+      float o[HD];
+      {
+        mbar_wait(&o_full[x], (nblk_done + nblk - 1) & 1u);
+        tc_fence_after();
+        uint32_t v[HD];
+        tmem_ld32(to, v);
+        tmem_ld32(to + 32, v + 32);
+        tmem_ld16(to + 64, v + 64);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < HD; ++i) o[i] = __uint_as_float(v[i]);
+        tc_fence_before();
+      }
       nblk_done += nblk;
 
       // ---- normalise, stage [128 x 80] bf16 (two 40-column boxes, 80-byte rows: conflict-free) in the P buffer
