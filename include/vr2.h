@@ -143,9 +143,22 @@ int32_t vr2_tower_get_precision(const vr2_tower* tower);
  * 0 means no activation was clamped: the result is what unbounded-range fp16 arithmetic would give.  reset != 0
  * zeroes the counter (stream-ordered).  Always 0 in the other precisions. */
 int vr2_tower_saturation_count(vr2_tower* tower, uint64_t* count_host, int32_t reset, void* stream);
-/* The same counter copied, stream-ordered and without synchronising, to a 4-byte destination in pinned host or device
- * memory: a pipelined caller snapshots it behind every forward and compares neighbours once the batch is complete. */
+/* The same, per conversion site: counts_host[VR2_SAT_SITES] =
+ *   [0] xb, the residual-stream operand x * w_norm written by the patch-embed / proj / down epilogues,
+ *   [1] q / k / v,   [2] h = silu(gate) * up,   [3] the merger's ln_q output and fc1 hidden. */
+#define VR2_SAT_SITES 4
+int vr2_tower_saturation_counts(vr2_tower* tower, uint64_t* counts_host, int32_t reset, void* stream);
+/* The VR2_SAT_SITES counters copied (uint32 each), stream-ordered and without synchronising, to a 16-byte destination
+ * in pinned host or device memory: a pipelined caller snapshots them behind every forward and compares neighbours
+ * once the batch is complete. */
 int vr2_tower_saturation_snapshot(vr2_tower* tower, uint32_t* dst, void* stream);
+/* Range shifts of VR2_PRECISION_F16, for checkpoints whose residual stream or SwiGLU products exceed fp16's range
+ * (massive activations): xb is stored times 2^-shift_xb and h times 2^-shift_h, and the consuming GEMMs' epilogues
+ * multiply the fp32 accumulator back (powers of two: exact; values below 2^(shift - 14) lose relative precision,
+ * far below the fp16 rounding of the O(1) entries).  Same instructions, same speed; the default 0 / 0 is bit-identical
+ * to the unshifted arithmetic.  Synchronises the device (the scaled norm-weight / bias copies are rebuilt). */
+int vr2_tower_set_f16_shift(vr2_tower* tower, int32_t shift_xb, int32_t shift_h);
+int vr2_tower_get_f16_shift(const vr2_tower* tower, int32_t* shifts_host /* [2] */);
 void vr2_tower_destroy(vr2_tower* tower);
 /* One call per entry of the HF module's state_dict (names relative to the
  * vision module: "patch_embed.proj.weight", "blocks.0.norm1.weight",

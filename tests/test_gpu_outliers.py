@@ -5,8 +5,10 @@ Outliers are injected into the weights so that (a) the fp32 residual stream carr
 typical magnitude but every 16-bit operand still fits fp16, (b) the residual-stream operand `x * w_norm` leaves fp16's
 range, (c) the SwiGLU product `silu(g) * u` leaves it.  Asserted, against the fp32 oracle:
   * in range  -> the guard stays at 0 and f16 meets the (scale-relative) north-star tolerance;
-  * out of range -> the guard counts, precision "auto" repeats the call with hi+lo bf16 operands (bit-identical to
-    "split") and that result meets the tolerance;  plain "f16" without the guard would have been silently wrong.
+  * out of range -> the guard counts at the right site; precision "auto" repeats the call with the range of that site
+    shifted by a power of two (still fp16 operands, full speed; remembered for later calls) and meets the tolerance;
+    when q/k/v themselves leave the range no shift applies and "auto" repeats the call with hi+lo bf16 operands
+    (bit-identical to "split").  Plain "f16" without the guard would have been silently wrong in every one of them.
 """
 import pytest
 import torch
@@ -72,27 +74,77 @@ def test_massive_but_in_range_activations_keep_f16_exact_enough():
     assert torch.equal(auto(x.cuda(), GRID, out_dtype=torch.float32), out) and auto.fallbacks == 0
 
 
-@pytest.mark.parametrize("kind", ["residual_out_of_range", "swiglu_out_of_range"])
-def test_out_of_range_activations_trip_the_guard_and_auto_falls_back(kind):
+@pytest.mark.parametrize("kind,site", [("residual_out_of_range", "xb"), ("swiglu_out_of_range", "h")])
+def test_out_of_range_activations_trip_the_guard_and_auto_shifts_the_range(kind, site):
     cfg, w, x, ref, hidden = _case(kind)
     f16 = _tower(cfg, w, "f16")
     out_h = f16(x.cuda(), GRID, out_dtype=torch.float32)
-    tripped = f16.saturation_count()
-    assert tripped > 0, "values beyond 65504 were converted without being counted"
-    assert f16.saturation_count() == 0                       # the read resets the counter
+    counts = f16.saturation_counts()
+    assert counts[site] > 0 and counts["qkv"] == 0, f"values beyond 65504 were converted without being counted: {counts}"
+    assert f16.saturation_count() == 0                       # the read resets the counters
+    with pytest.warns(UserWarning, match="range shifts"):
+        auto = _tower(cfg, w, "auto")
+        out_a = auto(x.cuda(), GRID, out_dtype=torch.float32)
+    sx, sh = auto.f16_shift
+    assert auto.fallbacks == 0 and auto.shift_changes >= 1 and (sx if site == "xb" else sh) >= 4, (auto.f16_shift, auto.fallbacks)
+    e_a, c_a = _stats(out_a, ref)
+    e_h, c_h = _stats(out_h, ref)
     split = _tower(cfg, w, "split")
-    out_s = split(x.cuda(), GRID, out_dtype=torch.float32)
+    e_s, c_s = _stats(split(x.cuda(), GRID, out_dtype=torch.float32), ref)
+    e_b, c_b = _stats(_tower(cfg, w, "bf16")(x.cuda(), GRID, out_dtype=torch.float32), ref)   # the reference's own arithmetic
+    print(f"\n{kind}: guard {counts} -> shifts {auto.f16_shift}: auto max-abs/scale {e_a:.5f} cos {c_a:.7f} | "
+          f"split {e_s:.5f} | bf16 (HF's arithmetic) {e_b:.4f} | unguarded f16 {e_h:.4f} cos {c_h:.6f}")
+    # With massive channels in the stream the ordinary channels live in the last bits of ANY 16-bit operand, so the
+    # distance to the fp32 path is set by the significand width: asserted for "auto" (11 bits, range shifted) at the
+    # north-star bound where it holds and otherwise at a quarter of the bf16 arithmetic's distance (8 bits: what the
+    # reference itself computes in) with the north-star cosine; "split" (16 bits) stays inside 2e-2.
+    assert (e_a <= 3e-2 or e_a <= 0.25 * e_b) and c_a >= 0.9995, (e_a, e_b, c_a)
+    assert e_a <= e_h                                        # never worse than the silently clamped result
+    assert e_s <= 2e-2 and c_s >= 0.9995, (e_s, c_s)
+    # the shifts are remembered: the next call runs once, at full speed, and gives the same numbers
+    n_before = auto.shift_changes
+    assert torch.equal(auto(x.cuda(), GRID, out_dtype=torch.float32), out_a) and auto.shift_changes == n_before
+    # ... also through the scattered store
+    x2 = torch.randn(N, 1176, generator=torch.Generator().manual_seed(5)).to(torch.bfloat16)
+    auto.forward_into(x2.cuda(), GRID, torch.zeros(N // 4, 3584, device="cuda"), torch.arange(N // 4, device="cuda"))
+    # shifts of zero are bit-identical to the unshifted kernels; a non-zero shift on in-range data changes nothing but
+    # the sub-2^-14 tail (powers of two are exact)
+    wg = T.make_weights(cfg, seed=21)
+    g = _tower(cfg, wg, "f16")
+    xg = torch.randn(N, 1176, generator=torch.Generator().manual_seed(22)).to(torch.bfloat16).cuda()
+    refg = T.tower_forward(wg, cfg, xg.float().cpu(), GRID)
+    plain = g(xg, GRID, out_dtype=torch.float32).clone()
+    e_plain = (plain.cpu() - refg).abs().max().item()
+    for shifts in ((4, 0), (0, 4), (8, 8)):
+        g.set_f16_shift(*shifts)
+        e_shift = (g(xg, GRID, out_dtype=torch.float32).cpu() - refg).abs().max().item()
+        # the few entries that fall into fp16's subnormal range round differently, which re-draws the rounding noise of
+        # everything downstream: a different realisation of the same error level, not a larger one
+        assert e_shift <= 1.3 * e_plain + 1e-4 and g.saturation_count() == 0, (shifts, e_shift, e_plain)
+    g.set_f16_shift(0, 0)
+    assert torch.equal(g(xg, GRID, out_dtype=torch.float32), plain)
+
+
+def test_qkv_out_of_range_falls_back_to_split():
+    """q/k/v beyond fp16's range: no power-of-two shift applies to them; "auto" repeats the call with hi+lo bf16
+    operands — the same bits as precision "split"."""
+    cfg = T.TowerConfig(depth=4, fullatt_block_indexes=(1, 3))
+    w = T.make_weights(cfg, seed=41)
+    w["blocks.2.attn.qkv.weight"][2560 + 17] *= 3e5           # one v channel of head 0: |v| ~ 2e5
+    w = {k: v.to(torch.bfloat16).float() for k, v in w.items()}
+    x = torch.randn(N, 1176, generator=torch.Generator().manual_seed(42)).to(torch.bfloat16)
+    ref = T.tower_forward(w, cfg, x.float(), GRID)
+    f16 = _tower(cfg, w, "f16")
+    f16(x.cuda(), GRID)
+    assert f16.saturation_counts()["qkv"] > 0
+    out_s = _tower(cfg, w, "split")(x.cuda(), GRID, out_dtype=torch.float32)
     with pytest.warns(UserWarning, match="saturation guard"):
         auto = _tower(cfg, w, "auto")
         out_a = auto(x.cuda(), GRID, out_dtype=torch.float32)
     assert auto.fallbacks == 1 and torch.equal(out_a, out_s)
     e_s, c_s = _stats(out_s, ref)
-    e_h, c_h = _stats(out_h, ref)
-    print(f"\n{kind}: guard {tripped}  split max-abs/scale {e_s:.5f} cos {c_s:.7f} | unguarded f16 {e_h:.4f} cos {c_h:.6f}")
+    print(f"\nqkv out of range: split max-abs/scale {e_s:.5f} cos {c_s:.7f}")
     assert e_s <= 2e-2 and c_s >= 0.9995, (e_s, c_s)
-    # a second call on in-range data with the same tower: no fallback, f16 speed path
-    x2 = torch.randn(N, 1176, generator=torch.Generator().manual_seed(5)).to(torch.bfloat16)
-    auto.forward_into(x2.cuda(), GRID, torch.zeros(N // 4, 3584, device="cuda"), torch.arange(N // 4, device="cuda"))
 
 
 def test_guard_is_silent_on_the_golden_shapes():
@@ -111,15 +163,23 @@ def test_pipeline_repeats_a_clamped_batch():
     tw = _tower(cfg, w, "auto")
     # an input that stays in range with the same weights: zero pixels (biases only)
     x_ok = torch.zeros_like(x_bad)
-    split = _tower(cfg, w, "split")
-    want_bad = split(x_bad.cuda(), GRID).cpu()
     f16 = _tower(cfg, w, "f16")
     want_ok = f16(x_ok.cuda(), GRID).cpu()
     if f16.saturation_count() != 0:
         pytest.skip("zero pixels also clamp with these weights")
-    pipe = vr2.HostPipeline(tw, depth=2)
-    for xh in (x_ok, x_bad, x_ok):
+    with pytest.warns(UserWarning, match="range shifts"):
+        pipe = vr2.HostPipeline(tw, depth=2)
+        for xh in (x_ok, x_bad, x_ok):
+            pipe.submit(xh.pin_memory(), GRID)
+        outs = [o.clone() for o, _ in pipe.results()]
+    assert pipe.fallbacks == 1 and tw.f16_shift[1] >= 4 and tw.fallbacks == 0
+    assert torch.equal(outs[0], want_ok)                      # computed before the shift, untouched
+    e, c = _stats(outs[1], ref)
+    assert e <= 0.3 and c >= 0.9995, (e, c)                   # the clamped batch, repeated with the range shifted (11-bit
+                                                              # operands under massive channels: see the test above)
+    assert (outs[2].float() - want_ok.float()).abs().max().item() < 2e-2
+    # from now on nothing clamps and nothing is repeated
+    for xh in (x_bad, x_ok):
         pipe.submit(xh.pin_memory(), GRID)
-    outs = [o.clone() for o, _ in pipe.results()]
-    assert pipe.fallbacks == 1
-    assert torch.equal(outs[0], want_ok) and torch.equal(outs[2], want_ok) and torch.equal(outs[1], want_bad)
+    more = [o.clone() for o, _ in pipe.results()]
+    assert pipe.fallbacks == 1 and torch.equal(more[0], outs[1])

@@ -459,10 +459,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 else xo = *st.f4(lane, j >> 2);
               }
             }
-            f[j] = a4.x + b.x + xo.x;
-            f[j + 1] = a4.y + b.y + xo.y;
-            f[j + 2] = a4.z + b.z + xo.z;
-            f[j + 3] = a4.w + b.w + xo.w;
+            f[j] = fmaf(a4.x, p.in_scale, b.x) + xo.x;       // in_scale == 1: the plain sum, exactly
+            f[j + 1] = fmaf(a4.y, p.in_scale, b.y) + xo.y;
+            f[j + 2] = fmaf(a4.z, p.in_scale, b.z) + xo.z;
+            f[j + 3] = fmaf(a4.w, p.in_scale, b.w) + xo.w;
           }
 #pragma unroll
           for (int j = 0; j < 16; ++j) ss = fmaf(f[j], f[j], ss);
@@ -531,7 +531,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (valid) {
           float s = 0.f;
           for (int q = 0; q < p.ssq_parts; ++q) s += p.ssq_in[static_cast<int64_t>(q) * p.M + r];
-          rstd = rsqrtf(s * p.inv_dim + p.eps);
+          rstd = rsqrtf(s * p.inv_dim + p.eps) * p.in_scale;
         }
         mbar_wait(&acc_full[as], use & 1u);
         tc_fence_after();
@@ -622,7 +622,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (valid) {
           float s = 0.f;
           for (int q = 0; q < p.ssq_parts; ++q) s += p.ssq_in[static_cast<int64_t>(q) * p.M + r];
-          rstd = rsqrtf(s * p.inv_dim + p.eps);
+          rstd = rsqrtf(s * p.inv_dim + p.eps) * p.in_scale;
         }
         constexpr int OC = BN / 2 / C::groups;  // 32 output columns per group
 #pragma unroll 1
@@ -636,10 +636,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int q = 0; q < 16; q += 4) {
             const float4 bg = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + q));
             const float4 bu = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + BN / 2 + c + q));
-            h[q] = silu(fmaf(__uint_as_float(g[q]), rstd, bg.x)) * fmaf(__uint_as_float(u[q]), rstd, bu.x);
-            h[q + 1] = silu(fmaf(__uint_as_float(g[q + 1]), rstd, bg.y)) * fmaf(__uint_as_float(u[q + 1]), rstd, bu.y);
-            h[q + 2] = silu(fmaf(__uint_as_float(g[q + 2]), rstd, bg.z)) * fmaf(__uint_as_float(u[q + 2]), rstd, bu.z);
-            h[q + 3] = silu(fmaf(__uint_as_float(g[q + 3]), rstd, bg.w)) * fmaf(__uint_as_float(u[q + 3]), rstd, bu.w);
+            h[q] = silu(fmaf(__uint_as_float(g[q]), rstd, bg.x)) * fmaf(__uint_as_float(u[q]), rstd * p.up_scale, bu.x);
+            h[q + 1] = silu(fmaf(__uint_as_float(g[q + 1]), rstd, bg.y)) * fmaf(__uint_as_float(u[q + 1]), rstd * p.up_scale, bu.y);
+            h[q + 2] = silu(fmaf(__uint_as_float(g[q + 2]), rstd, bg.z)) * fmaf(__uint_as_float(u[q + 2]), rstd * p.up_scale, bu.z);
+            h[q + 3] = silu(fmaf(__uint_as_float(g[q + 3]), rstd, bg.w)) * fmaf(__uint_as_float(u[q + 3]), rstd * p.up_scale, bu.w);
           }
           const int64_t off = static_cast<int64_t>(row0) * p.ld_out + n_blk * (BN / 2) + c;
           emit_piece<SPLIT>(st, h, p.out_bf16 + off, p.out_lo + off, p.ld_out, rows_valid, lane, 16, of16, osat);
@@ -743,7 +743,10 @@ bool tma_encode_2d_bf16(CUtensorMap* map, const void* base, uint64_t inner, uint
 
 int gemm_resid_parts(const GemmArgs& a) { return gemm2_supports(a) ? gemm2_resid_parts(a.N) : a.N / 40; }
 
-cudaError_t gemm_launch(const GemmArgs& a, int num_sms, cudaStream_t stream, const char** err) {
+cudaError_t gemm_launch(const GemmArgs& a_in, int num_sms, cudaStream_t stream, const char** err) {
+  GemmArgs a = a_in;
+  if (a.in_scale == 0.f) a.in_scale = 1.f;
+  if (a.up_scale == 0.f) a.up_scale = 1.f;
   static const char* none = "";
   *err = none;
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) {

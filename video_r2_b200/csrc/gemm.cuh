@@ -69,6 +69,12 @@ struct GemmArgs {
   // saturate, so the element-wise scan only runs for rows that might)
   unsigned int* sat;
   float sat_wmax2;
+  // f16 mode's range shifts (powers of two; 0 is read as 1): the A operand of this GEMM was stored scaled by
+  // 1 / in_scale, so the accumulator is multiplied back (EPI_QKV / EPI_SWIGLU: folded into rstd; EPI_RESID: acc *
+  // in_scale + bias + x).  up_scale (EPI_SWIGLU): the `up` half is produced times up_scale, i.e. h is stored scaled,
+  // with the caller passing an up-bias that is already multiplied by it — no extra instruction per element.
+  float in_scale;
+  float up_scale;
   // EPI_STORE_MULTI: destination buffers (row pitch ld_out each), device or peer-mapped device memory
   void* multi_out[kMaxMultiOut];
   int n_multi;

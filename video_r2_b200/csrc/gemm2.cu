@@ -406,10 +406,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col + 4 * j));
             const float4 w = __ldg(reinterpret_cast<const float4*>(p.norm_w + n0 + col + 4 * j));
             float4 f;
-            f.x = __uint_as_float(v[4 * j]) + bi.x + xo.x;
-            f.y = __uint_as_float(v[4 * j + 1]) + bi.y + xo.y;
-            f.z = __uint_as_float(v[4 * j + 2]) + bi.z + xo.z;
-            f.w = __uint_as_float(v[4 * j + 3]) + bi.w + xo.w;
+            f.x = fmaf(__uint_as_float(v[4 * j]), p.in_scale, bi.x) + xo.x;       // in_scale == 1: the plain sum, exactly
+            f.y = fmaf(__uint_as_float(v[4 * j + 1]), p.in_scale, bi.y) + xo.y;
+            f.z = fmaf(__uint_as_float(v[4 * j + 2]), p.in_scale, bi.z) + xo.z;
+            f.w = fmaf(__uint_as_float(v[4 * j + 3]), p.in_scale, bi.w) + xo.w;
             ss = fmaf(f.x, f.x, ss); ss = fmaf(f.y, f.y, ss); ss = fmaf(f.z, f.z, ss); ss = fmaf(f.w, f.w, ss);
             *xp = f;                                                         // new residual, in place
             pk[2 * j] = pack16x2<V>(f.x * w.x, f.y * w.y);                   // next GEMM's operand: x * w_norm
@@ -442,7 +442,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (valid) {
           float s = 0.f;
           for (int q = 0; q < p.ssq_parts; ++q) s += p.ssq_in[static_cast<int64_t>(q) * p.M + r];
-          rstd = rsqrtf(s * p.inv_dim + p.eps);
+          rstd = rsqrtf(s * p.inv_dim + p.eps) * p.in_scale;
         }
         int hw = 0;
         if (valid) hw = __ldg(p.pos_win + r);                       // this row's (h, w) position in its frame
@@ -561,8 +561,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (valid) {
           float s = 0.f;
           for (int q = 0; q < p.ssq_parts; ++q) s += p.ssq_in[static_cast<int64_t>(q) * p.M + r];
-          rstd = rsqrtf(s * p.inv_dim + p.eps);
+          rstd = rsqrtf(s * p.inv_dim + p.eps) * p.in_scale;
         }
+        const float rstd_u = rstd * p.up_scale;   // h = silu(g) * (u * up_scale): stored scaled, the up-bias comes pre-scaled
         if (local > 0) mbar_wait(&out_free[0], (local - 1) & 1u);   // the previous tile's store has drained
         mbar_wait_relaxed(&acc_full[as], use & 1u);
         tc_fence_after();
@@ -581,10 +582,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int q = 0; q < 16; q += 4) {
             const float4 bg = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c + q));
             const float4 bu = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + BN / 2 + c + q));
-            h[q] = silu(fmaf(__uint_as_float(g[q]), rstd, bg.x)) * fmaf(__uint_as_float(u[q]), rstd, bu.x);
-            h[q + 1] = silu(fmaf(__uint_as_float(g[q + 1]), rstd, bg.y)) * fmaf(__uint_as_float(u[q + 1]), rstd, bu.y);
-            h[q + 2] = silu(fmaf(__uint_as_float(g[q + 2]), rstd, bg.z)) * fmaf(__uint_as_float(u[q + 2]), rstd, bu.z);
-            h[q + 3] = silu(fmaf(__uint_as_float(g[q + 3]), rstd, bg.w)) * fmaf(__uint_as_float(u[q + 3]), rstd, bu.w);
+            h[q] = silu(fmaf(__uint_as_float(g[q]), rstd, bg.x)) * fmaf(__uint_as_float(u[q]), rstd_u, bu.x);
+            h[q + 1] = silu(fmaf(__uint_as_float(g[q + 1]), rstd, bg.y)) * fmaf(__uint_as_float(u[q + 1]), rstd_u, bu.y);
+            h[q + 2] = silu(fmaf(__uint_as_float(g[q + 2]), rstd, bg.z)) * fmaf(__uint_as_float(u[q + 2]), rstd_u, bu.z);
+            h[q + 3] = silu(fmaf(__uint_as_float(g[q + 3]), rstd, bg.w)) * fmaf(__uint_as_float(u[q + 3]), rstd_u, bu.w);
           }
           if constexpr (V == 1) {
 #pragma unroll
@@ -699,7 +700,10 @@ bool gemm2_supports(const GemmArgs& a) {
 
 int gemm2_resid_parts(int n) { return n / 256; }
 
-cudaError_t gemm2_launch(const GemmArgs& a, int num_sms, cudaStream_t stream, const char** err) {
+cudaError_t gemm2_launch(const GemmArgs& a_in, int num_sms, cudaStream_t stream, const char** err) {
+  GemmArgs a = a_in;
+  if (a.in_scale == 0.f) a.in_scale = 1.f;
+  if (a.up_scale == 0.f) a.up_scale = 1.f;
   const bool f16 = (a.flags & GEMM_OUT_F16) != 0;
   switch (a.epilogue) {
     case EPI_QKV: return f16 ? launch2<EPI_QKV, 1>(a, num_sms, stream, err) : launch2<EPI_QKV, 0>(a, num_sms, stream, err);

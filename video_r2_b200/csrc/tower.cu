@@ -69,8 +69,17 @@ struct vr2_tower {
   vr2::Tensor fc2_w, fc2_b;        // bf16 [out, md], fp32 [out]
   vr2::Tensor fc1_h, fc2_h;        // fp16 copies (VR2_PRECISION_F16)
   bool f16_ready = false;          // the fp16 copies reflect the current weights
-  unsigned int* sat = nullptr;     // device counter: fp16 conversions that saturated (f16 mode's range guard)
+  // f16 mode's range guard: device counters of fp16 conversions that saturated, one per site
+  //   [0] xb (the residual-stream operand x * w_norm)   [1] q/k/v   [2] h (SwiGLU product)   [3] merger (ln_q output, fc1 hidden)
+  unsigned int* sat = nullptr;
   std::vector<float> norm_wmax2;   // [2 * depth + 1] largest squared weight of norm1[l], norm2[l], ..., ln_q (finalize)
+  // f16 mode's range shifts: xb is stored times 2^-shift_xb (its consumers multiply rstd by 2^shift_xb), h times
+  // 2^-shift_h (the down GEMM's epilogue multiplies its accumulator by 2^shift_h).  Powers of two: exact.  They are
+  // applied through pre-scaled COPIES of the norm weights / up-biases, so the kernels spend no instruction on them.
+  int shift_xb = 0, shift_h = 0;
+  std::vector<std::vector<float>> norm_host;   // [2 * depth + 1][hidden] host copies (finalize)
+  std::vector<std::vector<float>> gub_host;    // [depth][2 * ipad]
+  std::vector<vr2::Tensor> norm_s, gub_s;      // device copies scaled for the current shifts (set_f16_shift)
   std::vector<void*> allocs;
   // optional per-kind CUDA-event timing (vr2_tower_profile)
   uint32_t prof_mask = 0;
@@ -221,7 +230,7 @@ extern "C" int vr2_tower_create(const vr2_tower_config* cfg, int32_t device, vr2
   }
   if (rc == VR2_OK) {
     Tensor c;
-    rc = alloc_zero(t, &c, 64);
+    rc = alloc_zero(t, &c, 64);   // VR2_SAT_SITES counters
     t->sat = static_cast<unsigned int*>(c.ptr);
   }
   if (rc != VR2_OK) {
@@ -331,21 +340,31 @@ extern "C" int vr2_tower_finalize(vr2_tower* t) {
   // largest squared RMSNorm weight per norm vector: the bound the residual epilogues' f16 range guard uses
   {
     const size_t h = t->cfg.hidden_size;
-    std::vector<float> buf(h);
-    auto wmax2 = [&](const Tensor& w, float* out) -> int {
-      VR2_CUDA(cudaMemcpy(buf.data(), w.ptr, h * sizeof(float), cudaMemcpyDeviceToHost));
+    const int n_norm = 2 * t->cfg.depth + 1;
+    t->norm_host.assign(n_norm, std::vector<float>(h));
+    t->norm_wmax2.assign(n_norm, 0.f);
+    auto wmax2 = [&](const Tensor& w, int i) -> int {
+      VR2_CUDA(cudaMemcpy(t->norm_host[i].data(), w.ptr, h * sizeof(float), cudaMemcpyDeviceToHost));
       float m = 0.f;
-      for (float v : buf) m = std::max(m, v * v);
-      *out = m;
+      for (float v : t->norm_host[i]) m = std::max(m, v * v);
+      t->norm_wmax2[i] = m;
       return VR2_OK;
     };
-    t->norm_wmax2.assign(2 * t->cfg.depth + 1, 0.f);
     int rc;
+    t->gub_host.assign(t->cfg.depth, std::vector<float>(2 * static_cast<size_t>(t->ipad)));
     for (int l = 0; l < t->cfg.depth; ++l) {
-      if ((rc = wmax2(t->layers[l].norm1_w, &t->norm_wmax2[2 * l])) != VR2_OK) return rc;
-      if ((rc = wmax2(t->layers[l].norm2_w, &t->norm_wmax2[2 * l + 1])) != VR2_OK) return rc;
+      if ((rc = wmax2(t->layers[l].norm1_w, 2 * l)) != VR2_OK) return rc;
+      if ((rc = wmax2(t->layers[l].norm2_w, 2 * l + 1)) != VR2_OK) return rc;
+      VR2_CUDA(cudaMemcpy(t->gub_host[l].data(), t->layers[l].gu_b.ptr, t->gub_host[l].size() * sizeof(float),
+                          cudaMemcpyDeviceToHost));
     }
-    if ((rc = wmax2(t->lnq_w, &t->norm_wmax2[2 * t->cfg.depth])) != VR2_OK) return rc;
+    if ((rc = wmax2(t->lnq_w, 2 * t->cfg.depth)) != VR2_OK) return rc;
+    if (t->shift_xb != 0 || t->shift_h != 0) {   // weights changed under non-zero shifts: rebuild the scaled copies
+      const int sx = t->shift_xb, sh = t->shift_h;
+      t->shift_xb = t->shift_h = 0;
+      t->finalized = true;
+      if ((rc = vr2_tower_set_f16_shift(t, sx, sh)) != VR2_OK) return rc;
+    }
   }
   t->finalized = true;
   return VR2_OK;
@@ -447,7 +466,8 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
   const char* msg = "";
   auto G = [&](GemmArgs& a, int kind, const char* what) -> int {
     ProfScope prof(t, kind, s);
-    a.sat = f16 ? t->sat : nullptr;
+    const int site = a.epilogue == EPI_QKV ? 1 : a.epilogue == EPI_SWIGLU ? 2 : a.epilogue == EPI_RESID ? 0 : 3;
+    a.sat = f16 ? t->sat + site : nullptr;
     if (a.epilogue == EPI_RESID) parts = gemm_resid_parts(a);
     cudaError_t e = gemm_launch(a, t->num_sms, s, &msg);
     if (e != cudaSuccess) return fail(e == cudaErrorInvalidValue ? VR2_ERR_ARG : VR2_ERR_CUDA, "vr2_tower_forward: %s: %s %s", what, cudaGetErrorString(e), msg);
@@ -457,6 +477,11 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
   const int act_in = f16 ? GEMM_A_F16 : 0, act_out = f16 ? GEMM_OUT_F16 : 0;
   if (f16 && (rc0 = ensure_f16_weights(t, s)) != VR2_OK) return rc0;
   auto WT = [&](const Tensor& w_bf16, const Tensor& w_f16) { return static_cast<const __nv_bfloat16*>(f16 ? w_f16.ptr : w_bf16.ptr); };
+  // range shifts of the f16 mode (vr2_tower_set_f16_shift): scaled norm-weight / up-bias copies, accumulator factors
+  const int sx = f16 ? t->shift_xb : 0, sh = f16 ? t->shift_h : 0;
+  const float xb_back = ldexpf(1.f, sx), h_back = ldexpf(1.f, sh), h_down = ldexpf(1.f, -sh);
+  auto NW = [&](int i, const Tensor& plain) { return static_cast<const float*>(sx != 0 ? t->norm_s[i].ptr : plain.ptr); };
+  auto NWMAX2 = [&](int i) { return t->norm_wmax2[i] * ldexpf(1.f, -2 * sx); };
   const __nv_bfloat16* pix = static_cast<const __nv_bfloat16*>(pixels);
   if (pixels_dtype == VR2_F32) {
     ProfScope prof(t, VR2_K_CAST, s);
@@ -472,8 +497,8 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
     a.epilogue = EPI_RESID; a.flags = act_out;
     a.x = w.x; a.ldx = h; a.out_bf16 = w.xb; a.out_lo = w.xb_lo; a.ld_out = h;
     a.row_map = plan->row_map;
-    a.norm_w = static_cast<const float*>(t->layers[0].norm1_w.ptr);
-    a.sat_wmax2 = t->norm_wmax2[0];
+    a.norm_w = NW(0, t->layers[0].norm1_w);
+    a.sat_wmax2 = NWMAX2(0);
     a.ssq = w.ssq;
     if ((rc = G(a, VR2_K_PATCH_EMBED, "patch_embed")) != VR2_OK) return rc;
   }
@@ -488,6 +513,7 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
       a.bias = static_cast<const float*>(L.qkv_b.ptr);
       a.out_bf16 = w.qkv; a.out_lo = w.qkv_lo; a.ld_out = 3 * h;
       a.ssq_in = w.ssq; a.ssq_parts = parts; a.inv_dim = 1.0f / h; a.eps = eps;
+      a.in_scale = xb_back;
       a.cos_tab = plan->cos_tab; a.sin_tab = plan->sin_tab;
       a.pos_win = plan->pos_win; a.pos_tab = plan->pos_tab; a.n_pos = plan->n_pos;
       if ((rc = G(a, VR2_K_QKV, "qkv")) != VR2_OK) return rc;
@@ -510,8 +536,8 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
       a.epilogue = EPI_RESID; a.flags = GEMM_ADD_RESID | act_in | act_out;
       a.bias = static_cast<const float*>(L.proj_b.ptr);
       a.x = w.x; a.ldx = h; a.out_bf16 = w.xb; a.out_lo = w.xb_lo; a.ld_out = h;
-      a.norm_w = static_cast<const float*>(L.norm2_w.ptr);
-      a.sat_wmax2 = t->norm_wmax2[2 * l + 1];
+      a.norm_w = NW(2 * l + 1, L.norm2_w);
+      a.sat_wmax2 = NWMAX2(2 * l + 1);
       a.ssq = w.ssq;
       if ((rc = G(a, VR2_K_PROJ, "proj")) != VR2_OK) return rc;
     }
@@ -520,9 +546,10 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
       a.A = w.xb; a.A_lo = w.xb_lo; a.lda = h; a.W = WT(L.gu_w, L.gu_h); a.ldw = h;
       a.M = static_cast<int>(N); a.N = 2 * t->ipad; a.K = h;
       a.epilogue = EPI_SWIGLU; a.flags = act_in | act_out;
-      a.bias = static_cast<const float*>(L.gu_b.ptr);
+      a.bias = static_cast<const float*>(sh != 0 ? t->gub_s[l].ptr : L.gu_b.ptr);
       a.out_bf16 = w.hbuf; a.out_lo = w.hbuf_lo; a.ld_out = t->ipad;
       a.ssq_in = w.ssq; a.ssq_parts = parts; a.inv_dim = 1.0f / h; a.eps = eps;
+      a.in_scale = xb_back; a.up_scale = h_down;
       if ((rc = G(a, VR2_K_GATE_UP, "gate_up")) != VR2_OK) return rc;
     }
     {
@@ -532,8 +559,9 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
       a.epilogue = EPI_RESID; a.flags = GEMM_ADD_RESID | act_in | act_out;
       a.bias = static_cast<const float*>(L.down_b.ptr);
       a.x = w.x; a.ldx = h; a.out_bf16 = w.xb; a.out_lo = w.xb_lo; a.ld_out = h;
-      a.norm_w = static_cast<const float*>(l + 1 < t->cfg.depth ? t->layers[l + 1].norm1_w.ptr : t->lnq_w.ptr);
-      a.sat_wmax2 = t->norm_wmax2[2 * l + 2];
+      a.norm_w = NW(2 * l + 2, l + 1 < t->cfg.depth ? t->layers[l + 1].norm1_w : t->lnq_w);
+      a.sat_wmax2 = NWMAX2(2 * l + 2);
+      a.in_scale = h_back;
       a.ssq = w.ssq;
       if ((rc = G(a, VR2_K_DOWN, "down")) != VR2_OK) return rc;
     }
@@ -545,7 +573,7 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
   {
     ProfScope prof(t, VR2_K_MERGER_NORM, s);
     VR2_CUDA(rmsnorm_to_bf16(w.x, static_cast<const float*>(t->lnq_w.ptr), w.qkv, w.qkv_lo, N, h, eps, s, f16,
-                             f16 ? t->sat : nullptr));
+                             f16 ? t->sat + 3 : nullptr));
   }
   {
     GemmArgs a{};
@@ -621,18 +649,82 @@ extern "C" int32_t vr2_tower_get_precision(const vr2_tower* t) { return t == nul
 
 extern "C" int vr2_tower_saturation_snapshot(vr2_tower* t, uint32_t* dst, void* stream_v) {
   if (t == nullptr || dst == nullptr) return fail(VR2_ERR_ARG, "vr2_tower_saturation_snapshot: null argument");
-  VR2_CUDA(cudaMemcpyAsync(dst, t->sat, sizeof(uint32_t), cudaMemcpyDefault, as_stream(stream_v)));
+  VR2_CUDA(cudaMemcpyAsync(dst, t->sat, VR2_SAT_SITES * sizeof(uint32_t), cudaMemcpyDefault, as_stream(stream_v)));
+  return VR2_OK;
+}
+
+extern "C" int vr2_tower_saturation_counts(vr2_tower* t, uint64_t* counts_host, int32_t reset, void* stream_v) {
+  if (t == nullptr || counts_host == nullptr) return fail(VR2_ERR_ARG, "vr2_tower_saturation_counts: null argument");
+  cudaStream_t s = as_stream(stream_v);
+  unsigned int v[VR2_SAT_SITES] = {0, 0, 0, 0};
+  VR2_CUDA(cudaMemcpyAsync(v, t->sat, sizeof(v), cudaMemcpyDeviceToHost, s));
+  if (reset) VR2_CUDA(cudaMemsetAsync(t->sat, 0, sizeof(v), s));
+  VR2_CUDA(cudaStreamSynchronize(s));
+  for (int i = 0; i < VR2_SAT_SITES; ++i) counts_host[i] = v[i];
   return VR2_OK;
 }
 
 extern "C" int vr2_tower_saturation_count(vr2_tower* t, uint64_t* count_host, int32_t reset, void* stream_v) {
   if (t == nullptr || count_host == nullptr) return fail(VR2_ERR_ARG, "vr2_tower_saturation_count: null argument");
-  cudaStream_t s = as_stream(stream_v);
-  unsigned int v = 0;
-  VR2_CUDA(cudaMemcpyAsync(&v, t->sat, sizeof(v), cudaMemcpyDeviceToHost, s));
-  if (reset) VR2_CUDA(cudaMemsetAsync(t->sat, 0, sizeof(v), s));
-  VR2_CUDA(cudaStreamSynchronize(s));
-  *count_host = v;
+  uint64_t v[VR2_SAT_SITES];
+  const int rc = vr2_tower_saturation_counts(t, v, reset, stream_v);
+  if (rc != VR2_OK) return rc;
+  *count_host = v[0] + v[1] + v[2] + v[3];
+  return VR2_OK;
+}
+
+extern "C" int vr2_tower_set_f16_shift(vr2_tower* t, int32_t shift_xb, int32_t shift_h) {
+  if (t == nullptr) return fail(VR2_ERR_ARG, "vr2_tower_set_f16_shift: null tower");
+  if (!t->finalized) return fail(VR2_ERR_STATE, "vr2_tower_set_f16_shift: weights not finalized");
+  if (shift_xb < 0 || shift_xb > 14 || shift_h < 0 || shift_h > 14)
+    return fail(VR2_ERR_ARG, "vr2_tower_set_f16_shift: shifts must be in [0, 14], got %d / %d", shift_xb, shift_h);
+  int prev = -1;
+  VR2_CUDA(cudaGetDevice(&prev));
+  VR2_CUDA(cudaSetDevice(t->device));
+  int rc = VR2_OK;
+  auto upload = [&](Tensor* dst, const std::vector<float>& v) -> int {
+    if (dst->ptr == nullptr) {
+      void* p = nullptr;
+      VR2_CUDA(cudaMalloc(&p, v.size() * sizeof(float)));
+      t->allocs.push_back(p);
+      dst->ptr = p;
+    }
+    VR2_CUDA(cudaMemcpy(dst->ptr, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));   // orders after prior work
+    return VR2_OK;
+  };
+  VR2_CUDA(cudaDeviceSynchronize());   // no forward may be reading the copies that are about to change
+  if (shift_xb != 0) {
+    t->norm_s.resize(t->norm_host.size());
+    const float c = ldexpf(1.f, -shift_xb);
+    std::vector<float> tmp;
+    for (size_t i = 0; i < t->norm_host.size() && rc == VR2_OK; ++i) {
+      tmp = t->norm_host[i];
+      for (float& v : tmp) v *= c;
+      rc = upload(&t->norm_s[i], tmp);
+    }
+  }
+  if (shift_h != 0 && rc == VR2_OK) {
+    t->gub_s.resize(t->gub_host.size());
+    const float c = ldexpf(1.f, -shift_h);
+    std::vector<float> tmp;
+    for (size_t l = 0; l < t->gub_host.size() && rc == VR2_OK; ++l) {
+      tmp = t->gub_host[l];
+      for (size_t j = 0; j < tmp.size(); ++j)
+        if (j % 256 >= 128) tmp[j] *= c;      // the `up` half of every 256-column gate|up tile
+      rc = upload(&t->gub_s[l], tmp);
+    }
+  }
+  cudaSetDevice(prev);
+  if (rc != VR2_OK) return rc;
+  t->shift_xb = shift_xb;
+  t->shift_h = shift_h;
+  return VR2_OK;
+}
+
+extern "C" int vr2_tower_get_f16_shift(const vr2_tower* t, int32_t* shifts_host) {
+  if (t == nullptr || shifts_host == nullptr) return fail(VR2_ERR_ARG, "vr2_tower_get_f16_shift: null argument");
+  shifts_host[0] = t->shift_xb;
+  shifts_host[1] = t->shift_h;
   return VR2_OK;
 }
 

@@ -59,8 +59,8 @@ class HostPipeline:
         # f16 range guard (tower precision "auto" / "f16"): the counter is snapshotted behind every forward into pinned
         # host memory; results() compares neighbouring snapshots and repeats a clamped batch in the split precision
         self._guard = tower.precision in ("auto", "f16") and gather_counts is None
-        self._snap = torch.zeros(self._SNAPS, dtype=torch.int32).pin_memory() if self._guard else None   # ring, one per submit
-        self._snap_seen = 0
+        self._snap = torch.zeros((self._SNAPS, 4), dtype=torch.int32).pin_memory() if self._guard else None   # ring, one row per submit
+        self._snap_seen, self._seen_epoch, self._epoch = (0, 0, 0, 0), 0, 0   # counters restart (new epoch) after a redo
         if self._guard:
             tower.saturation_count(reset=True)
         self.fallbacks = 0
@@ -168,12 +168,12 @@ class HostPipeline:
             d2h = torch.cuda.Event()
             d2h.record(self.s_out)
         self._d2h_done[slot] = d2h
-        self._pending.append((d2h, out_host, pos_host, (self._n - 1) % self._SNAPS, (x_host, plan, _frames, _size)))
+        self._pending.append((d2h, out_host, pos_host, (self._n - 1) % self._SNAPS, self._epoch, (x_host, plan, _frames, _size)))
 
     @torch.no_grad()
     def _redo_split(self, out_host, x_host, plan, frames, size):
-        """Rare path: the f16 guard tripped on this batch.  Recompute it from the host input, synchronously, with
-        hi+lo bf16 operands, and overwrite its host result."""
+        """Rare path: the f16 guard tripped on this batch.  Recompute it from the host input, synchronously, under the
+        tower's "auto" policy (raise the range shifts, else hi+lo bf16 operands), and overwrite its host result."""
         self.fallbacks += 1
         cfg = self.tower.cfg
         x = x_host.to(self.dev)
@@ -183,9 +183,13 @@ class HostPipeline:
             x = patchify(x.contiguous(), patch_size=cfg.patch_size, temporal_patch_size=cfg.temporal_patch_size,
                          merge_size=cfg.spatial_merge_size)
         out = torch.empty((plan.num_tokens, cfg.out_hidden_size), dtype=out_host.dtype, device=self.dev)
-        self.tower.run_split(plan, x.contiguous(), out)
+        self.tower.saturation_counts(reset=True)
+        self.tower._launch(plan, x.contiguous(), out, None, check_guard=True)
         out_host.copy_(out)
         torch.cuda.current_stream(self.dev).synchronize()
+        # the counters restart from zero for everything submitted from now on (a new epoch); batches already in flight
+        # keep comparing against their own epoch's snapshots, and are redone in turn if they clamped too
+        self._epoch += 1
 
     def gathered(self, ago: int = 0) -> torch.Tensor:
         """Sharded mode: the all-gathered embeddings (device, valid in the compute stream's order) of the batch
@@ -197,12 +201,13 @@ class HostPipeline:
     def results(self):
         """Yields (embeddings_host, position_ids_host or None) in submission order."""
         while self._pending:
-            ev, out_host, pos_host, snap_i, redo = self._pending.popleft()
+            ev, out_host, pos_host, snap_i, epoch, redo = self._pending.popleft()
             ev.synchronize()
             if self._guard:
-                seen = int(self._snap[snap_i].item())   # cumulative counter right behind this batch's forward
-                if seen != self._snap_seen:
-                    self._snap_seen = seen
+                seen = tuple(self._snap[snap_i].tolist())   # cumulative counters right behind this batch's forward
+                prev = self._snap_seen if epoch == self._seen_epoch else (0, 0, 0, 0)
+                self._snap_seen, self._seen_epoch = seen, epoch
+                if seen != prev:
                     self._redo_split(out_host, *redo)
             yield out_host, pos_host
 

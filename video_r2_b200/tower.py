@@ -177,9 +177,13 @@ class VisionTower:
     def __init__(self, cfg: VisionConfig, state_dict, device="cuda:0", plan_cache: int = 16, precision=None):
         """precision:
           "auto"  (default) fp16 activations with the library's saturation guard: every forward is followed by a read of
-                  the guard counter (one 4-byte D2H + stream synchronisation, where HF's own forward has its `.tolist()`
-                  syncs) and is re-run in "split" if any activation left fp16's range.  Full speed and max-abs <= 2e-2
-                  against the fp32 reference on in-range activations; never silently clamped on outliers.
+                  the guard counters (one 16-byte D2H + stream synchronisation, where HF's own forward has its
+                  `.tolist()` syncs).  If an activation left fp16's range the call is repeated: first with the range
+                  SHIFTED at the site that clamped (the residual-stream operand and / or the SwiGLU product stored times
+                  2^-4, 2^-8, 2^-12 — exact, same speed, remembered for later calls: a checkpoint with massive
+                  activations pays for this once), and with hi+lo bf16 operands ("split") if q/k/v or the merger
+                  clamped or the shifts run out.  Full speed and max-abs <= 2e-2 against the fp32 reference; never
+                  silently clamped.
           "f16"   the same arithmetic without the read: the caller checks `saturation_count()` itself (pipelines, benchmarks).
           "split" hi + lo bf16 operands (~16 mantissa bits, bf16's range, 2x the MMA work); also meets 2e-2.
           "bf16"  activations rounded to bf16 once per GEMM input, as HF's own bf16 path (max-abs ~5e-2 after 32 blocks).
@@ -211,6 +215,7 @@ class VisionTower:
         self._emb_cache = collections.OrderedDict()   # embedding reuse, see forward(reuse=...)
         self.reuse_hits = 0
         self.fallbacks = 0             # "auto": forwards repeated in split because the f16 guard tripped
+        self.shift_changes = 0         # "auto": times the f16 range shifts were raised (each repeats one forward)
         self.set_precision(precision or os.environ.get("VR2_PRECISION", "auto"))
         self.load_state_dict(state_dict)
 
@@ -231,8 +236,30 @@ class VisionTower:
                   "vr2_tower_saturation_count")
         return int(n.value)
 
+    SAT_SITES = ("xb", "qkv", "h", "merger")
+
+    def saturation_counts(self, reset: bool = True) -> dict:
+        """The same per conversion site: {"xb": residual-stream operand, "qkv", "h": SwiGLU product, "merger"}."""
+        n = (C.c_uint64 * 4)()
+        with torch.cuda.device(self.device):
+            check(lib().vr2_tower_saturation_counts(self._h, n, 1 if reset else 0, _stream_ptr(self.device)),
+                  "vr2_tower_saturation_counts")
+        return {k: int(n[i]) for i, k in enumerate(self.SAT_SITES)}
+
+    @property
+    def f16_shift(self):
+        """(shift_xb, shift_h): the residual-stream operand is stored times 2^-shift_xb and the SwiGLU product times
+        2^-shift_h in the f16 / auto precisions (include/vr2.h vr2_tower_set_f16_shift)."""
+        v = (C.c_int32 * 2)()
+        check(lib().vr2_tower_get_f16_shift(self._h, v), "vr2_tower_get_f16_shift")
+        return int(v[0]), int(v[1])
+
+    def set_f16_shift(self, shift_xb: int, shift_h: int):
+        check(lib().vr2_tower_set_f16_shift(self._h, int(shift_xb), int(shift_h)), "vr2_tower_set_f16_shift")
+        self._emb_cache.clear()
+
     def saturation_snapshot(self, dst: torch.Tensor):
-        """Copies the guard counter into dst[0] (uint32/int32 tensor, pinned host or device) in stream order, no sync."""
+        """Copies the 4 guard counters into dst[0:4] (int32 tensor, pinned host or device) in stream order, no sync."""
         with torch.cuda.device(self.device):
             check(lib().vr2_tower_saturation_snapshot(self._h, dst.data_ptr(), _stream_ptr(self.device)),
                   "vr2_tower_saturation_snapshot")
@@ -352,8 +379,22 @@ class VisionTower:
         self._enqueue(plan, x, out, rows)
         if check_guard is None:
             check_guard = self.precision == "auto"
-        if check_guard and self.saturation_count(reset=True):
-            self.run_split(plan, x, out, rows)
+        if not check_guard:
+            return
+        counts = self.saturation_counts(reset=True)
+        while any(counts.values()):
+            sx, sh = self.f16_shift
+            nx = sx + self.SHIFT_STEP if counts["xb"] else sx
+            nh = sh + self.SHIFT_STEP if counts["h"] else sh
+            if counts["qkv"] or counts["merger"] or max(nx, nh) > self.SHIFT_MAX:
+                self.run_split(plan, x, out, rows)         # nothing a power-of-two shift can absorb
+                return
+            self.set_f16_shift(nx, nh)
+            self.shift_changes += 1
+            warnings.warn(f"video_r2_b200: activations left fp16's range at {[k for k, v in counts.items() if v]}; "
+                          f"range shifts (xb, h) are now 2^-{nx}, 2^-{nh} and the forward was repeated")
+            self._enqueue(plan, x, out, rows)
+            counts = self.saturation_counts(reset=True)
 
     def run_split(self, plan, x, out, rows=None):
         """Repeat a forward in the split precision (fallback of the f16 range guard), then return to the current one."""
@@ -413,6 +454,8 @@ class VisionTower:
         if not 1 <= len(dest_ptrs) <= 8:
             raise ValueError("forward_multi takes 1..8 destinations")
         self._launch(plan, x, dest_ptrs, None, check_guard)
+
+    SHIFT_STEP, SHIFT_MAX = 4, 12
 
     KERNEL_KINDS = ("cast", "patch_embed", "qkv", "attn_window", "attn_full", "proj", "gate_up", "down",
                     "merger_norm", "fc1", "fc2")
