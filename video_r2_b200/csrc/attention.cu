@@ -270,8 +270,9 @@ cudaError_t attention_launch(const __nv_bfloat16* qkv, const __nv_bfloat16* qkv_
     attn_varlen_kernel<true><<<grid, 128, 6 * kTile, stream>>>(qkv, qkv_lo, out, out_lo, tiles, ld_qkv, ld_out,
                                                                num_heads * HD, scale_log2);
   } else {
-    attn_varlen_kernel<false><<<grid, 128, 3 * kTile, stream>>>(qkv, nullptr, out, nullptr, tiles, ld_qkv, ld_out,
-                                                                num_heads * HD, scale_log2);
+    // single-operand attention runs on the tcgen05 kernel (attention2.cu); this mma.sync kernel is kept for the hi + lo
+    // operands of the split precision only
+    return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
 }
