@@ -312,6 +312,26 @@ int vr2_mrope_apply(const void* q_dev, const void* k_dev, void* q_out_dev, void*
                     int32_t S, int32_t Hq, int32_t Hk, int32_t D, const int64_t* position_ids_dev,
                     const float* inv_freq_dev, const int32_t* mrope_section_host, float attention_scaling, void* stream);
 
+/* The same rotation FUSED into the decoder's q | k | v projection (the consumer side of
+ * vr2_rope_index inside the LLM: Qwen2_5_VLAttention.forward, modeling_qwen2_5_vl.py:627-669 — q_proj / k_proj / v_proj
+ * (Linear with bias), `.view(B, S, heads, 128)`, apply_multimodal_rotary_pos_emb on q and k):
+ *
+ *   vr2_mrope_table        once per decoder forward: cos / sin of the 64 rotary angles of every token, fp32
+ *                          [B*S, head_dim/2] each, mrope_section axis choice applied (what Qwen2_5_VLRotaryEmbedding.
+ *                          forward + the split / cat of apply_multimodal_rotary_pos_emb produce, never cast to bf16);
+ *   vr2_decoder_qkv_mrope  per layer: out[M, N] = bf16(rot(hidden[M, K] · wqkv[N, K]^T + bias)) on the CTA-pair tcgen05
+ *                          GEMM; wqkv / bias are the q, k, v projections concatenated along N (N = (Hq + 2 Hkv) * 128);
+ *                          columns < rot_cols (= (Hq + Hkv) * 128) are rotated head by head with pairs (d, d + 64), in
+ *                          fp32 on the accumulator, rounded to bf16 once.  q = out[:, :Hq*128].view(B, S, Hq, 128)
+ *                          .transpose(1, 2) etc. are the (strided) tensors HF has at that point.
+ * hidden / wqkv bf16, 16-byte aligned; N % 256 == 0; head_dim 128.  More accurate than the reference's own bf16
+ * pipeline (which rounds after the Linear, after each product and after the sum): compared against fp32 in the tests. */
+int vr2_mrope_table(const int64_t* position_ids_dev, int32_t B, int32_t S, const float* inv_freq_dev, int32_t half_dim,
+                    const int32_t* mrope_section_host, float attention_scaling, float* cos_dev, float* sin_dev, void* stream);
+int vr2_decoder_qkv_mrope(const void* hidden_dev, const void* wqkv_dev, const float* bias_dev, int64_t M, int32_t N, int32_t K,
+                          int32_t head_dim, int32_t rot_cols, const float* cos_dev, const float* sin_dev, void* out_dev,
+                          void* stream);
+
 /* ------------------------------------------------------------------------
  * LM-head per-token log-probabilities without materialising the logits.
  * out[m] = log_softmax(hidden[m] @ W^T / temperature)[target[m]], fp32.  Replaces, in Video-R2's GRPO

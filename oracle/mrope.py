@@ -26,3 +26,18 @@ def apply_mrope(q, k, position_ids, inv_freq, mrope_section=(16, 24, 24), attent
     cos = torch.cat([m[i % 3] for i, m in enumerate(cos.split(sec, dim=-1))], dim=-1).unsqueeze(1)
     sin = torch.cat([m[i % 3] for i, m in enumerate(sin.split(sec, dim=-1))], dim=-1).unsqueeze(1)
     return (q * cos) + (rotate_half(q) * sin), (k * cos) + (rotate_half(k) * sin)
+
+
+def decoder_qkv(hidden, wq, bq, wk, bk, wv, bv, position_ids, inv_freq, mrope_section=(16, 24, 24), head_dim=128,
+                dtype=torch.float32):
+    """The first lines of `Qwen2_5_VLAttention.forward` (modeling_qwen2_5_vl.py:627-669): q/k/v = Linear(hidden) viewed
+    as [B, heads, S, head_dim], multimodal rotary on q and k — every operation in `dtype` (float32: the reference the
+    fused kernel is judged against; bfloat16: what the reference model itself computes, roundings included)."""
+    import torch.nn.functional as F
+    B, S, _ = hidden.shape
+    x = hidden.to(dtype)
+    q = F.linear(x, wq.to(dtype), bq.to(dtype)).view(B, S, -1, head_dim).transpose(1, 2)
+    k = F.linear(x, wk.to(dtype), bk.to(dtype)).view(B, S, -1, head_dim).transpose(1, 2)
+    v = F.linear(x, wv.to(dtype), bv.to(dtype)).view(B, S, -1, head_dim).transpose(1, 2)
+    q, k = apply_mrope(q, k, position_ids, inv_freq, mrope_section)
+    return q, k, v

@@ -96,6 +96,8 @@ SIGNATURES = {
                                     C.c_int32, C.c_int32, _P, C.c_int32, _P, _P]),
     "vr2_mrope_apply": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P,
                                   C.POINTER(C.c_int32), C.c_float, _P]),
+    "vr2_mrope_table": (C.c_int, [_P, C.c_int32, C.c_int32, _P, C.c_int32, C.POINTER(C.c_int32), C.c_float, _P, _P, _P]),
+    "vr2_decoder_qkv_mrope": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     "vr2_lm_logprob_workspace_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "vr2_lm_logprob": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, C.c_float, _P, _P, C.c_size_t, _P]),
     "vr2_tower_saturation_count": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_int32, _P]),

@@ -773,6 +773,7 @@ cudaError_t gemm_launch(const GemmArgs& a_in, int num_sms, cudaStream_t stream, 
         }
         break;
       case EPI_LOGPROB:
+      case EPI_MROPE:
         break;
       default:
         if (a.bias == nullptr || a.ssq_in == nullptr || a.out_bf16 == nullptr) {
@@ -838,6 +839,9 @@ cudaError_t gemm_launch(const GemmArgs& a_in, int num_sms, cudaStream_t stream, 
       return launch_any<256, EPI_SWIGLU>(a, num_sms, stream, err);
     case EPI_LOGPROB:
       *err = "gemm: EPI_LOGPROB needs target / partial buffers (CTA-pair kernel only)";
+      return cudaErrorInvalidValue;
+    case EPI_MROPE:
+      *err = "gemm: EPI_MROPE needs N % 256 == 0, rot_cols % 128 == 0, cos / sin tables and an output (CTA-pair kernel only)";
       return cudaErrorInvalidValue;
     default:
       *err = "gemm: unknown epilogue";

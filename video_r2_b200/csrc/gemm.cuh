@@ -15,6 +15,9 @@ enum GemmEpilogue : int {
   EPI_QKV = 2,     // v = acc*rstd + bias; 2-D rotary on q,k heads; bf16 [M,3840]
   EPI_SWIGLU = 3,  // h = silu(g*rstd+bg) * (u*rstd+bu), gate/up interleaved per 256-column tile
   EPI_LOGPROB = 4, // LM head without logits: per (row, 256-column block) max / sum-exp of acc * inv_temp, target logit
+  EPI_MROPE = 6,   // decoder q|k|v projection with the multimodal rotary embedding fused (CTA-pair kernel): out =
+                   // bf16(rot(acc + bias)), heads of 128 columns, pairs (d, d + 64) rotated by per-row cos / sin tables
+                   // for columns < rot_cols (the q and k heads); v heads get the bias only
   EPI_STORE_MULTI = 5,  // out = acc + bias as bf16, each (row-mapped) row written to n_multi destination buffers
                         // (local + peer GPUs' copies of the result: the all-gather fused into the producing GEMM)
 };
@@ -75,6 +78,11 @@ struct GemmArgs {
   // with the caller passing an up-bias that is already multiplied by it — no extra instruction per element.
   float in_scale;
   float up_scale;
+  // EPI_MROPE: cos / sin of the 64 rotary angles of every row, fp32 [M, 64] each (vr2_mrope_table), and the number of
+  // leading output columns that are rotated
+  const float* mrope_cos;
+  const float* mrope_sin;
+  int rot_cols;
   // EPI_STORE_MULTI: destination buffers (row pitch ld_out each), device or peer-mapped device memory
   void* multi_out[kMaxMultiOut];
   int n_multi;

@@ -63,6 +63,12 @@ struct Cfg2<EPI_SWIGLU, V> {
                                                // store drains long before the next tile's accumulator is complete)
   static constexpr int aux_bytes = 0;
 };
+template <int V>
+struct Cfg2<EPI_MROPE, V> {
+  static constexpr int BN = 256, groups = 4, stages = 5;   // two heads of 128 per tile
+  static constexpr int out_bytes = 4 * 16384;              // 128 x 256 bf16 as four 128B-swizzled 64-column boxes
+  static constexpr int aux_bytes = 0;
+};
 // EPI_RESID moves its 128 x 256 tile through shared memory in eight sub-steps of 32 columns over four 24 KB buffers
 // (fp32 residual: one [128 x 32] box with 128-byte rows, SWIZZLE_128B, updated in place; bf16 operand: one [128 x 32]
 // box with 64-byte rows, SWIZZLE_64B), each buffer served by its own group of 4 epilogue warps (one per TMEM lane
@@ -336,6 +342,20 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         __syncwarp();
         if (issuer) mbar_arrive(&out_free[local & 1u]);
       }
+    } else if constexpr (EPI == EPI_MROPE) {
+      for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++local) {
+        const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
+        const int n0 = (tile % num_n) * BN;
+        mbar_wait(&store_ready[0], local & 1u);
+        if (issuer) {
+#pragma unroll
+          for (int b = 0; b < 4; ++b) tma_store_2d(&tm0, out_base + b * 16384, n0 + b * 64, m0);
+          tma_store_commit();
+          tma_store_wait_read<0>();
+          mbar_arrive(&out_free[0]);
+        }
+        __syncwarp();
+      }
     } else {  // EPI_SWIGLU
       for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++local) {
         const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
@@ -555,6 +575,67 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         // (max, sum) of this warp's 64 columns -> the item parity's slot; the store warp combines the 4 groups
         if (use > 0) mbar_wait(&out_free[as], (use - 1) & 1u);   // the store warp has consumed this slot's previous item
         reinterpret_cast<float2*>(aux_base)[(as * 4 + cg) * 128 + row] = make_float2(mx, sum);
+      } else if constexpr (EPI == EPI_MROPE) {
+        // tile = two heads of 128 columns; group cg owns head (cg >> 1) and the 32 rotary pairs (f, f + 64) with
+        // f in [32 (cg & 1), +32): both halves of a pair live in this thread's accumulator row
+        const int head = cg >> 1, f0 = (cg & 1) * 32;
+        const int hc = n0 + head * 128;                 // first output column of the head
+        const bool rot = hc < p.rot_cols;               // q and k heads rotate, v heads do not
+        if (local > 0) mbar_wait(&out_free[0], (local - 1) & 1u);   // the previous tile's stores have drained
+        mbar_wait_relaxed(&acc_full[as], use & 1u);
+        tc_fence_after();
+        // 128B-swizzled [128 x 64 bf16] boxes: 16-byte chunk index XOR (row & 7), as TMA SWIZZLE_128B expects
+        uint8_t* box_lo = out_base + (head * 2) * 16384 + row * 128;       // columns [0, 64) of the head
+        uint8_t* box_hi = box_lo + 16384;                                  // columns [64, 128)
+#pragma unroll 1
+        for (int i0 = 0; i0 < 32; i0 += 8) {
+          const int f = f0 + i0;
+          uint32_t lo[8], hi[8];
+          tmem_ld8(taddr + head * 128 + f, lo);
+          tmem_ld8(taddr + head * 128 + 64 + f, hi);
+          float cs[8], sn[8];
+          if (rot && valid) {
+            const float4 c0 = __ldg(reinterpret_cast<const float4*>(p.mrope_cos + static_cast<int64_t>(r) * 64 + f));
+            const float4 c1 = __ldg(reinterpret_cast<const float4*>(p.mrope_cos + static_cast<int64_t>(r) * 64 + f + 4));
+            const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.mrope_sin + static_cast<int64_t>(r) * 64 + f));
+            const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.mrope_sin + static_cast<int64_t>(r) * 64 + f + 4));
+            cs[0] = c0.x; cs[1] = c0.y; cs[2] = c0.z; cs[3] = c0.w; cs[4] = c1.x; cs[5] = c1.y; cs[6] = c1.z; cs[7] = c1.w;
+            sn[0] = s0.x; sn[1] = s0.y; sn[2] = s0.z; sn[3] = s0.w; sn[4] = s1.x; sn[5] = s1.y; sn[6] = s1.z; sn[7] = s1.w;
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { cs[q] = 1.f; sn[q] = 0.f; }
+          }
+          float ba[8], bb[8];
+          if (p.bias != nullptr) {
+            const float4 a0 = __ldg(reinterpret_cast<const float4*>(p.bias + hc + f));
+            const float4 a1 = __ldg(reinterpret_cast<const float4*>(p.bias + hc + f + 4));
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + hc + 64 + f));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + hc + 64 + f + 4));
+            ba[0] = a0.x; ba[1] = a0.y; ba[2] = a0.z; ba[3] = a0.w; ba[4] = a1.x; ba[5] = a1.y; ba[6] = a1.z; ba[7] = a1.w;
+            bb[0] = b0.x; bb[1] = b0.y; bb[2] = b0.z; bb[3] = b0.w; bb[4] = b1.x; bb[5] = b1.y; bb[6] = b1.z; bb[7] = b1.w;
+          } else {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { ba[q] = 0.f; bb[q] = 0.f; }
+          }
+          tmem_ld_wait();
+          float a[8], b[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float x1 = __uint_as_float(lo[q]) + ba[q], x2 = __uint_as_float(hi[q]) + bb[q];
+            a[q] = x1 * cs[q] - x2 * sn[q];      // q * cos + rotate_half(q) * sin, in fp32 (HF :149-167 does it in bf16)
+            b[q] = x2 * cs[q] + x1 * sn[q];
+          }
+          const int chunk = f >> 3;              // 16-byte chunk of the 128-byte box row
+          *reinterpret_cast<uint4*>(box_lo + ((chunk ^ (row & 7)) << 4)) =
+              make_uint4(pack_bf16x2(a[0], a[1]), pack_bf16x2(a[2], a[3]), pack_bf16x2(a[4], a[5]), pack_bf16x2(a[6], a[7]));
+          *reinterpret_cast<uint4*>(box_hi + ((chunk ^ (row & 7)) << 4)) =
+              make_uint4(pack_bf16x2(b[0], b[1]), pack_bf16x2(b[2], b[3]), pack_bf16x2(b[4], b[5]), pack_bf16x2(b[6], b[7]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(&acc_empty[as]); else mbar_arrive_cluster(acc_empty_leader + as * 8);
+        }
       } else {  // EPI_SWIGLU
         // tile columns [0,128) are gate rows, [128,256) the matching up rows; group cg owns 32 outputs
         float rstd = 0.f;
@@ -641,6 +722,10 @@ cudaError_t launch2(const GemmArgs& a, int num_sms, cudaStream_t stream, const c
     ok = ok && tma_encode_2d_swz(&tm0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a.x, a.N, a.M, a.ldx * 4, 32, BM, 128) &&
          tma_encode_2d_swz(&tm1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.out_bf16, a.N, a.M, a.ld_out * 2, 32, BM, 64);
     tm2 = tm1;
+  } else if (EPI == EPI_MROPE) {
+    ok = ok && encode(&tm0, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.out_bf16, a.N, a.M, a.ld_out * 2, 64, BM, true);
+    tm1 = tm0;
+    tm2 = tm0;
   } else if (EPI == EPI_LOGPROB) {
     tm0 = tmA;
     tm1 = tmA;
@@ -694,6 +779,7 @@ bool gemm2_supports(const GemmArgs& a) {
     case EPI_RESID: return (a.flags & GEMM_ADD_RESID) != 0 && a.N % 256 == 0 && a.bias != nullptr;
     case EPI_SWIGLU: return a.N % 256 == 0;
     case EPI_LOGPROB: return a.target != nullptr && a.part_max != nullptr && a.part_sum != nullptr && a.tgt_logit != nullptr;
+    case EPI_MROPE: return a.N % 256 == 0 && a.rot_cols % 128 == 0 && a.mrope_cos != nullptr && a.mrope_sin != nullptr && a.out_bf16 != nullptr;
     default: return false;
   }
 }
@@ -710,6 +796,7 @@ cudaError_t gemm2_launch(const GemmArgs& a_in, int num_sms, cudaStream_t stream,
     case EPI_RESID: return f16 ? launch2<EPI_RESID, 1>(a, num_sms, stream, err) : launch2<EPI_RESID, 0>(a, num_sms, stream, err);
     case EPI_SWIGLU: return f16 ? launch2<EPI_SWIGLU, 1>(a, num_sms, stream, err) : launch2<EPI_SWIGLU, 0>(a, num_sms, stream, err);
     case EPI_LOGPROB: return launch2<EPI_LOGPROB, 0>(a, num_sms, stream, err);
+    case EPI_MROPE: return launch2<EPI_MROPE, 0>(a, num_sms, stream, err);
     default: *err = "gemm2: unsupported epilogue"; return cudaErrorInvalidValue;
   }
 }

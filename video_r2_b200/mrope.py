@@ -66,3 +66,75 @@ def _apply(q, k, position_ids, inv_freq, mrope_section, attention_scaling, inpla
                                     inv.data_ptr(), sec, float(attention_scaling), _stream_ptr(q.device)),
               "vr2_mrope_apply")
     return qo, ko
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The rotation fused into the decoder's q | k | v projection (vr2_mrope_table + vr2_decoder_qkv_mrope)
+# ---------------------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def mrope_table(position_ids: torch.Tensor, inv_freq: torch.Tensor, mrope_section=(16, 24, 24), attention_scaling: float = 1.0):
+    """position_ids [3, B, S] int64 (CUDA) -> (cos, sin) fp32 [B*S, D/2]: the rotary angles of every token with the
+    mrope_section axis choice applied.  Computed once per decoder forward, shared by all layers."""
+    if not position_ids.is_cuda or position_ids.dim() != 3 or position_ids.shape[0] != 3:
+        raise ValueError("mrope_table: position_ids must be a CUDA tensor [3, B, S]")
+    _, B, S = position_ids.shape
+    pos = position_ids.to(torch.int64).contiguous()
+    inv = inv_freq.to(device=pos.device, dtype=torch.float32).contiguous()
+    half = inv.numel()
+    cos = torch.empty((B * S, half), dtype=torch.float32, device=pos.device)
+    sin = torch.empty_like(cos)
+    sec = (C.c_int32 * 3)(*[int(v) for v in mrope_section])
+    with torch.cuda.device(pos.device):
+        check(lib().vr2_mrope_table(pos.data_ptr(), B, S, inv.data_ptr(), half, sec, float(attention_scaling), cos.data_ptr(),
+                                    sin.data_ptr(), _stream_ptr(pos.device)), "vr2_mrope_table")
+    return cos, sin
+
+
+class FusedDecoderQKV:
+    """q_proj / k_proj / v_proj of one `Qwen2_5_VLAttention` (modeling_qwen2_5_vl.py:627-669) as ONE tcgen05 GEMM whose
+    epilogue adds the biases and applies the multimodal rotary embedding to the q and k heads.
+
+        fused = vr2.FusedDecoderQKV(attn.q_proj, attn.k_proj, attn.v_proj, head_dim=128)      # once per layer
+        cos, sin = vr2.mrope_table(position_ids, rotary_emb.inv_freq, mrope_section)           # once per forward
+        q, k, v = fused(hidden_states, cos, sin)      # [B, Hq, S, 128], [B, Hkv, S, 128], [B, Hkv, S, 128] (strided views)
+
+    FORWARD ONLY (prefill / generation, the no-grad reference and old-policy passes of GRPO): the weights are snapshotted
+    (concatenated, bf16) at construction, and a call with grad enabled on an input that requires grad raises."""
+
+    def __init__(self, q_proj, k_proj, v_proj, head_dim: int = 128):
+        ws = [m.weight.detach() for m in (q_proj, k_proj, v_proj)]
+        dev = ws[0].device
+        if dev.type != "cuda":
+            raise ValueError("FusedDecoderQKV: the projections must live on a CUDA device (no CPU path)")
+        self.head_dim = head_dim
+        self.nq, self.nk, self.nv = (w.shape[0] for w in ws)
+        self.K = ws[0].shape[1]
+        self.w = torch.cat([w.to(torch.bfloat16) for w in ws], dim=0).contiguous()
+        bs = [(m.bias.detach().float() if m.bias is not None else torch.zeros(m.weight.shape[0], device=dev)) for m in (q_proj, k_proj, v_proj)]
+        self.b = torch.cat(bs).contiguous()
+        self.N = self.w.shape[0]
+        if self.N % 256 or self.nq % head_dim or self.nk % head_dim or self.nv % head_dim:
+            raise ValueError(f"FusedDecoderQKV: q/k/v widths {self.nq}/{self.nk}/{self.nv} must be multiples of head_dim "
+                             f"{head_dim} and sum to a multiple of 256")
+
+    def __call__(self, hidden_states: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor):
+        if torch.is_grad_enabled() and hidden_states.requires_grad:
+            raise RuntimeError("FusedDecoderQKV is forward-only: use it under torch.no_grad() (prefill, generation, the "
+                               "reference / old-policy passes); keep the stock projections for the pass that is differentiated")
+        with torch.no_grad():
+            B, S, K = hidden_states.shape
+            if K != self.K or hidden_states.dtype != torch.bfloat16:
+                raise ValueError(f"FusedDecoderQKV: hidden_states must be bf16 [B, S, {self.K}]")
+            if cos.shape != (B * S, self.head_dim // 2) or cos.dtype != torch.float32:
+                raise ValueError(f"FusedDecoderQKV: cos / sin must be fp32 [{B * S}, {self.head_dim // 2}] (mrope_table)")
+            h = hidden_states.contiguous().view(B * S, K)
+            out = torch.empty((B * S, self.N), dtype=torch.bfloat16, device=h.device)
+            with torch.cuda.device(h.device):
+                check(lib().vr2_decoder_qkv_mrope(h.data_ptr(), self.w.data_ptr(), self.b.data_ptr(), B * S, self.N, K, self.head_dim,
+                                                  self.nq + self.nk, cos.contiguous().data_ptr(), sin.contiguous().data_ptr(),
+                                                  out.data_ptr(), _stream_ptr(h.device)), "vr2_decoder_qkv_mrope")
+            D = self.head_dim
+            q = out[:, :self.nq].view(B, S, self.nq // D, D).transpose(1, 2)
+            k = out[:, self.nq:self.nq + self.nk].view(B, S, self.nk // D, D).transpose(1, 2)
+            v = out[:, self.nq + self.nk:].view(B, S, self.nv // D, D).transpose(1, 2)
+            return q, k, v
