@@ -528,6 +528,42 @@ def run_vr2(args, rank, local_rank, world):
             del hl, wl, tl
         except Exception as e:  # never let the optional measurement break the contract line
             widening["lm_logprob"] = {"error": repr(e)}
+        # the decoder's q|k|v projection with M-RoPE fused into the GEMM epilogue, vs what the
+        # reference runs (three cuBLAS Linears + Hugging Face's rotary functions), Qwen2.5-VL-7B decoder geometry
+        try:
+            from transformers.models.qwen2_5_vl import modeling_qwen2_5_vl as HFM
+            Bq, Sq, Kq, Hq, Hk, Dq = 2, 4096, 3584, 28, 4, 128
+            gq = torch.Generator(device=dev).manual_seed(10)
+            hid = torch.randn(Bq, Sq, Kq, generator=gq, device=dev).to(torch.bfloat16)
+            lins = [torch.nn.Linear(Kq, n, bias=True, device=dev, dtype=torch.bfloat16) for n in (Hq * Dq, Hk * Dq, Hk * Dq)]
+            posq = torch.randint(0, 6000, (3, Bq, Sq), generator=gq, device=dev)
+            invq = (1.0 / (1000000.0 ** (torch.arange(0, Dq, 2, dtype=torch.int64).float() / Dq))).to(dev)
+            fusedq = vr2.FusedDecoderQKV(*lins, head_dim=Dq)
+
+            def qkv_fused(i):
+                c, s_ = vr2.mrope_table(posq, invq)
+                return fusedq(hid, c, s_)
+
+            def qkv_ref(i):    # Qwen2_5_VLRotaryEmbedding.forward + Qwen2_5_VLAttention.forward up to the rotary
+                with torch.no_grad():
+                    fr = (invq[None, None, :, None].float().expand(3, Bq, -1, 1) @ posq[:, :, None, :].float()).transpose(2, 3)
+                    emb = torch.cat((fr, fr), dim=-1)
+                    c, s_ = emb.cos().to(torch.bfloat16), emb.sin().to(torch.bfloat16)
+                    q_, k_, v_ = (l(hid).view(Bq, Sq, -1, Dq).transpose(1, 2) for l in lins)
+                    q_, k_ = HFM.apply_multimodal_rotary_pos_emb(q_, k_, c, s_, [16, 24, 24])
+                    return q_, k_, v_
+
+            for fn in (qkv_fused, qkv_ref):
+                fn(0)
+            ms_qf = timed(qkv_fused, 5) / 5
+            ms_qr = timed(qkv_ref, 5) / 5
+            dq = max((a_.float() - b_.float()).abs().max().item() for a_, b_ in zip(qkv_fused(0), qkv_ref(0)))
+            widening["decoder_qkv_mrope"] = {"tokens": Bq * Sq, "fused_ms": ms_qf, "linear_x3_plus_hf_rotary_ms": ms_qr,
+                                             "fused_tflops": 2.0 * Bq * Sq * Kq * (Hq + 2 * Hk) * Dq / (ms_qf * 1e-3) / 1e12,
+                                             "max_abs_diff_vs_bf16_pipeline": dq}
+            del hid, lins, fusedq
+        except Exception as e:
+            widening["decoder_qkv_mrope"] = {"error": repr(e)}
 
     # ---- the other BASELINE configs (outside the headline's timed region).  N = 1: the whole batch on this GPU.
     #      N > 1: STRONG-scaled through shard.encode_sharded — every rank holds the same pixels (GRPO's RepeatSampler
