@@ -165,3 +165,20 @@ def test_tall_frame_uses_per_row_rotary_tables():
         e, c, r = _stats(out, ref)
         print(f"\n{grid}: max-abs {e:.4f} cos {c:.6f}")
         assert e <= 3e-2 and c >= 0.9995, (grid, e, c)
+
+
+def test_grid_tensor_is_recognised_without_a_second_readback():
+    """The same `grid_thw` tensor object, unmodified, maps to its plan without another D2H; an in-place change of the
+    tensor (version bump) is seen."""
+    cfg = T.TowerConfig(depth=1, fullatt_block_indexes=(0,))
+    tower = _tower(cfg, T.make_weights(cfg, seed=2))
+    g = torch.tensor([[1, 4, 6]], device="cuda")
+    x = torch.randn(48, 1176, generator=torch.Generator().manual_seed(3)).to(torch.bfloat16).cuda()
+    a = tower(torch.cat([x[:24], x[:24]]), g.clone().mul_(torch.tensor([2, 1, 1], device="cuda"))).clone()   # [[2,4,6]]
+    p1 = tower.plan(g)
+    assert tower.plan(g) is p1 and id(g) in tower._grid_keys
+    b = tower(x[:24], g)
+    g[0, 0] = 2                                    # same object, new contents
+    p2 = tower.plan(g)
+    assert p2 is not p1 and p2.grid == ((2, 4, 6),)
+    assert torch.equal(tower(torch.cat([x[:24], x[:24]]), g), a) and b.shape[0] == 6

@@ -23,6 +23,8 @@
 // Replaces the cuBLAS calls behind HF modeling_qwen2_5_vl.py:221-287 (qkv, proj) and :87-88 (gate/up/down).
 #include "gemm.cuh"
 
+#include <cstdlib>
+
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -762,10 +764,22 @@ cudaError_t launch2(const GemmArgs& a, int num_sms, cudaStream_t stream, const c
       return cudaErrorInvalidValue;
     }
     max_clusters = n < num_sms / 2 ? n : num_sms / 2;
+    // experiments only (profiles/README.md): cap the number of co-resident CTA pairs, e.g. to see whether a launch is
+    // bound by the SMs it occupies or by what all of them share (L2)
+    const char* cap = getenv(EPI == EPI_RESID ? "VR2_GEMM2_MAX_CLUSTERS_RESID" : "VR2_GEMM2_MAX_CLUSTERS");
+    if (cap != nullptr) {
+      const int c = atoi(cap);
+      if (c > 0 && c < max_clusters) max_clusters = c;
+    }
   }
   const int pair_tiles = ((a.M + 2 * BM - 1) / (2 * BM)) * ((a.N + L::BN - 1) / L::BN);
+  // as many pairs as keep the number of waves: 320 residual tiles on 74 pairs are 5 waves with 24 pairs idle in the last
+  // one; 64 pairs do the same 5 tiles each with less contention for what the launch is bound by (L2): measured -2 % on
+  // proj, -1 % on down, and a tensor-bound launch (gate|up: 1728 tiles, 24 waves on 72 or 74 pairs) loses nothing
   int clusters = max_clusters;
   if (pair_tiles < clusters) clusters = pair_tiles;
+  const int waves = (pair_tiles + clusters - 1) / clusters;
+  clusters = (pair_tiles + waves - 1) / waves;
   gemm2_kernel<EPI, V><<<2 * clusters, L::threads, L::smem_bytes, stream>>>(tmA, tmB, tm0, tm1, tm2, a);
   return cudaGetLastError();
 }

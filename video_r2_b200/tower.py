@@ -210,6 +210,7 @@ class VisionTower:
         self._h = handle
         self._plans = collections.OrderedDict()
         self._plan_cache = plan_cache
+        self._grid_keys = {}           # id(grid_thw tensor) -> (weakref, version, values): skips the D2H for a tensor seen before
         self._ws = None
         self._ws_split = None          # workspace of the split fallback (twice the size), kept once allocated
         self._emb_cache = collections.OrderedDict()   # embedding reuse, see forward(reuse=...)
@@ -293,7 +294,17 @@ class VisionTower:
         if isinstance(grid_thw, Plan):
             return grid_thw
         if isinstance(grid_thw, torch.Tensor):
-            key = tuple(grid_thw.detach().to("cpu", torch.int64).reshape(-1).tolist())
+            # the values are needed on the host (they size the output): one small D2H, as HF's own `.tolist()`.  The same
+            # tensor OBJECT, unmodified, is recognised without it — GRPO passes one `video_grid_thw` through its
+            # generate / reference / policy forwards (grpo_trainer.py:783, :826-833, :1094)
+            hit = self._grid_keys.get(id(grid_thw))
+            if hit is not None and hit[0]() is grid_thw and hit[1] == grid_thw._version:
+                key = hit[2]
+            else:
+                key = tuple(grid_thw.detach().to("cpu", torch.int64).reshape(-1).tolist())
+                if len(self._grid_keys) > 64:
+                    self._grid_keys.clear()
+                self._grid_keys[id(grid_thw)] = (weakref.ref(grid_thw), grid_thw._version, key)
         else:
             key = tuple(int(v) for row in grid_thw for v in row)
         p = self._plans.get(key)
