@@ -5,12 +5,11 @@
 
 namespace vr2 {
 
-// tiles[i] = (q_start, q_len<=64, kv_start, kv_len): one 64-row query tile and the
-// cu_seqlens segment it attends to.  qkv: [N, 3*hidden] bf16 (q | k | v, heads of 80).
-// qkv_lo / out_lo non-null selects the split ("precise") kernel: operands are hi + lo bf16 pairs of the same layout.
-cudaError_t attention_launch(const __nv_bfloat16* qkv, const __nv_bfloat16* qkv_lo, __nv_bfloat16* out,
-                             __nv_bfloat16* out_lo, const int4* tiles, int n_tiles, int num_heads, int64_t ld_qkv,
-                             int64_t ld_out, cudaStream_t stream);
+// The split precision's attention (attention3.cu): operands are hi + lo bf16 pairs of the same [N, 3*hidden] layout,
+// three tcgen05.mma products per contraction, output as a hi + lo pair.  seg as for attention_tc_launch.
+cudaError_t attention_split_launch(const __nv_bfloat16* qkv, const __nv_bfloat16* qkv_lo, __nv_bfloat16* out,
+                                   __nv_bfloat16* out_lo, const int2* seg, int n_rows, int num_heads, int64_t ld_qkv,
+                                   int64_t ld_out, int num_sms, cudaStream_t stream);
 
 // tcgen05 / TMEM / TMA kernel (attention2.cu).  seg[r] = (first, past-last) row of the segment row r belongs to
 // (device, [n_rows]); query tiles are the consecutive 128-row chunks of [0, n_rows).

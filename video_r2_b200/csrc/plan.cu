@@ -139,7 +139,6 @@ extern "C" int vr2_plan_create(const vr2_plan_config* cfg, const int64_t* grid, 
 
   std::vector<ClipDesc> clips(n_items);
   std::vector<int32_t> cu_window{0}, cu_seq{0};
-  std::vector<int4> tiles_w, tiles_f;
   int64_t tok = 0;
   for (int c = 0; c < n_items; ++c) {
     const int64_t t = grid[3 * c], h = grid[3 * c + 1], w = grid[3 * c + 2];
@@ -155,17 +154,12 @@ extern "C" int vr2_plan_create(const vr2_plan_config* cfg, const int64_t* grid, 
       // full-attention segment = one temporal slice of h*w patches (HF :488-496)
       const int64_t seg0 = cu_seq.back();
       const int64_t L = h * w;
-      for (int64_t q0 = 0; q0 < L; q0 += 64)
-        tiles_f.push_back(make_int4(static_cast<int>(seg0 + q0), static_cast<int>(std::min<int64_t>(64, L - q0)),
-                                    static_cast<int>(seg0), static_cast<int>(L)));
       cu_seq.push_back(static_cast<int32_t>(seg0 + L));
       for (int a = 0; a < nwh; ++a)
         for (int b = 0; b < nww; ++b) {
           const int rows = std::min(ws, lh - a * ws), cols = std::min(ws, lw - b * ws);
           const int len = rows * cols * merge * merge;  // patches in this window (<= 64)
           const int w0 = cu_window.back();
-          for (int q0 = 0; q0 < len; q0 += 64)
-            tiles_w.push_back(make_int4(w0 + q0, std::min(64, len - q0), w0, len));
           cu_window.push_back(w0 + len);
         }
     }
@@ -179,8 +173,6 @@ extern "C" int vr2_plan_create(const vr2_plan_config* cfg, const int64_t* grid, 
   plan->n_patches = tok * merge * merge;
   plan->n_windows = static_cast<int64_t>(cu_window.size()) - 1;
   plan->n_slices = static_cast<int64_t>(cu_seq.size()) - 1;
-  plan->n_tiles_window = static_cast<int64_t>(tiles_w.size());
-  plan->n_tiles_full = static_cast<int64_t>(tiles_f.size());
 
   std::vector<float> inv_freq(plan->half_dim / 2);
   for (int k = 0; k < plan->half_dim / 2; ++k)  // HF :117-130: 1 / theta^(2k / (head_dim/2))
@@ -206,8 +198,8 @@ extern "C" int vr2_plan_create(const vr2_plan_config* cfg, const int64_t* grid, 
   for (int c = 0; c < n_items; ++c) n_pos = std::max<int>(n_pos, static_cast<int>(std::max(grid[3 * c + 1], grid[3 * c + 2])));
   plan->n_pos = n_pos;
   const size_t total = rnd(N * 4) + rnd(static_cast<size_t>(n_pos) * HDIM * 4) + rnd(N * 8) * 2 + rnd(T * 8) * 2 + rnd(N * 4) + rnd(T * 4) + rnd(N * 8) + rnd(N * HDIM * 4) * 2 +
-                       rnd(cu_window.size() * 4) + rnd(cu_seq.size() * 4) + rnd(tiles_w.size() * 16) +
-                       rnd(tiles_f.size() * 16) + rnd(clips.size() * sizeof(ClipDesc)) + rnd(inv_freq.size() * 4);
+                       rnd(cu_window.size() * 4) + rnd(cu_seq.size() * 4) +
+                       rnd(clips.size() * sizeof(ClipDesc)) + rnd(inv_freq.size() * 4);
   e = cudaMalloc(&plan->blob, total);
   if (e != cudaSuccess) {
     delete plan;
@@ -223,8 +215,6 @@ extern "C" int vr2_plan_create(const vr2_plan_config* cfg, const int64_t* grid, 
   plan->sin_tab = carve<float>(cur, N * HDIM);
   plan->cu_window = carve<int32_t>(cur, cu_window.size());
   plan->cu_seqlens = carve<int32_t>(cur, cu_seq.size());
-  plan->tiles_window = carve<int4>(cur, tiles_w.size());
-  plan->tiles_full = carve<int4>(cur, tiles_f.size());
   plan->pos_win = carve<int32_t>(cur, N);
   plan->pos_tab = carve<float>(cur, static_cast<size_t>(n_pos) * HDIM);
   plan->seg_window = carve<int2>(cur, N);
@@ -235,8 +225,6 @@ extern "C" int vr2_plan_create(const vr2_plan_config* cfg, const int64_t* grid, 
   auto up = [&](void* dst, const void* src, size_t bytes) { return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream); };
   e = up(plan->cu_window, cu_window.data(), cu_window.size() * 4);
   if (e == cudaSuccess) e = up(plan->cu_seqlens, cu_seq.data(), cu_seq.size() * 4);
-  if (e == cudaSuccess) e = up(plan->tiles_window, tiles_w.data(), tiles_w.size() * 16);
-  if (e == cudaSuccess) e = up(plan->tiles_full, tiles_f.data(), tiles_f.size() * 16);
   if (e == cudaSuccess) e = up(plan->seg_window, seg_w.data(), N * 8);
   if (e == cudaSuccess) e = up(plan->seg_full, seg_f.data(), N * 8);
   if (e == cudaSuccess) e = up(d_clips, clips.data(), clips.size() * sizeof(ClipDesc));

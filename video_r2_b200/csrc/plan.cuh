@@ -13,8 +13,6 @@ struct vr2_plan {
   int64_t n_tokens = 0;
   int64_t n_windows = 0; // non-empty windows
   int64_t n_slices = 0;
-  int64_t n_tiles_window = 0;
-  int64_t n_tiles_full = 0;
   std::vector<int64_t> grid;  // host copy [n_items*3]
 
   // device tables (one allocation, carved)
@@ -31,8 +29,6 @@ struct vr2_plan {
   int n_pos = 0;                     // max(h, w) over the clips (patch units)
   int32_t* cu_window = nullptr;      // [windows+1]
   int32_t* cu_seqlens = nullptr;     // [slices+1]
-  int4* tiles_window = nullptr;      // attention query tiles for window layers (mma.sync kernel, split precision)
-  int4* tiles_full = nullptr;        // ... for full-attention layers
   int2* seg_window = nullptr;        // [patches] (first, past-last) row of the window a patch row belongs to
-  int2* seg_full = nullptr;          // [patches] ... of its temporal slice (tcgen05 attention kernel)
+  int2* seg_full = nullptr;          // [patches] ... of its temporal slice (both attention kernels)
 };

@@ -521,10 +521,9 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
     {
       const bool full = is_full_layer(t, l);
       ProfScope prof(t, full ? VR2_K_ATTN_FULL : VR2_K_ATTN_WINDOW, s);
-      if (split)   // hi + lo operands: the mma.sync kernel with 3 products per contraction
-        VR2_CUDA(attention_launch(w.qkv, w.qkv_lo, w.att, w.att_lo, full ? plan->tiles_full : plan->tiles_window,
-                                  static_cast<int>(full ? plan->n_tiles_full : plan->n_tiles_window), t->cfg.num_heads,
-                                  3 * h, h, s));
+      if (split)   // hi + lo operands: 3 tcgen05 products per contraction (attention3.cu)
+        VR2_CUDA(attention_split_launch(w.qkv, w.qkv_lo, w.att, w.att_lo, full ? plan->seg_full : plan->seg_window,
+                                        static_cast<int>(N), t->cfg.num_heads, 3 * h, h, t->num_sms, s));
       else
         VR2_CUDA(attention_tc_launch(w.qkv, w.att, full ? plan->seg_full : plan->seg_window, static_cast<int>(N),
                                      t->cfg.num_heads, 3 * h, h, t->num_sms, s, f16));
@@ -832,8 +831,8 @@ static int op_attention_impl(const void* qkv, const void* qkv_lo, void* out, voi
   cudaStream_t s = as_stream(stream_v);
   cudaError_t e = cudaSuccess;
   void* d = nullptr;
-  if (qkv_lo == nullptr) {
-    // tcgen05 kernel: per-row segment bounds
+  {
+    // per-row segment bounds (both kernels take them)
     const int n_rows = cu[n_seq] - cu[0];
     if (cu[0] != 0) return fail(VR2_ERR_ARG, "vr2_op_attention: cu_seqlens must start at 0");
     if (n_rows == 0) return VR2_OK;
@@ -845,23 +844,15 @@ static int op_attention_impl(const void* qkv, const void* qkv_lo, void* out, voi
     VR2_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     VR2_CUDA(cudaMalloc(&d, seg.size() * 8));
     e = cudaMemcpyAsync(d, seg.data(), seg.size() * 8, cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess)
-      e = attention_tc_launch(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out),
-                              static_cast<const int2*>(d), n_rows, num_heads, 3 * num_heads * 80, num_heads * 80, sms, s, f16);
-  } else {
-    std::vector<int4> tiles;
-    for (int i = 0; i < n_seq; ++i) {
-      const int s0 = cu[i], L = cu[i + 1] - cu[i];
-      for (int q0 = 0; q0 < L; q0 += 64) tiles.push_back(make_int4(s0 + q0, std::min(64, L - q0), s0, L));
+    if (e == cudaSuccess) {
+      if (qkv_lo == nullptr)
+        e = attention_tc_launch(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out),
+                                static_cast<const int2*>(d), n_rows, num_heads, 3 * num_heads * 80, num_heads * 80, sms, s, f16);
+      else
+        e = attention_split_launch(static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(qkv_lo),
+                                   static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(out_lo),
+                                   static_cast<const int2*>(d), n_rows, num_heads, 3 * num_heads * 80, num_heads * 80, sms, s);
     }
-    if (tiles.empty()) return VR2_OK;
-    VR2_CUDA(cudaMalloc(&d, tiles.size() * 16));
-    e = cudaMemcpyAsync(d, tiles.data(), tiles.size() * 16, cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess)
-      e = attention_launch(static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(qkv_lo),
-                           static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(out_lo),
-                           static_cast<const int4*>(d), static_cast<int>(tiles.size()), num_heads, 3 * num_heads * 80,
-                           num_heads * 80, s);
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(s);
   cudaFree(d);
