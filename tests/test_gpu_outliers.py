@@ -175,8 +175,10 @@ def test_pipeline_repeats_a_clamped_batch():
     assert pipe.fallbacks == 1 and tw.f16_shift[1] >= 4 and tw.fallbacks == 0
     assert torch.equal(outs[0], want_ok)                      # computed before the shift, untouched
     e, c = _stats(outs[1], ref)
-    assert e <= 0.3 and c >= 0.9995, (e, c)                   # the clamped batch, repeated with the range shifted (11-bit
-                                                              # operands under massive channels: see the test above)
+    # the clamped batch, repeated with the range shifted.  11-bit operands under 1e5-fold outlier channels: 0.2-0.35 of the
+    # output scale depending on the summation order, where the bf16 arithmetic the reference computes in is at 5.3 and the
+    # silently clamped result at 2.2 (see the test above)
+    assert e <= 0.6 and c >= 0.9995, (e, c)
     assert (outs[2].float() - want_ok.float()).abs().max().item() < 2e-2
     # from now on nothing clamps and nothing is repeated
     for xh in (x_bad, x_ok):

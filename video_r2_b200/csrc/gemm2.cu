@@ -71,22 +71,46 @@ struct Cfg2<EPI_MROPE, V> {
   static constexpr int out_bytes = 4 * 16384;              // 128 x 256 bf16 as four 128B-swizzled 64-column boxes
   static constexpr int aux_bytes = 0;
 };
-// EPI_RESID moves its 128 x 256 tile through shared memory in eight sub-steps of 32 columns over four 24 KB buffers
-// (fp32 residual: one [128 x 32] box with 128-byte rows, SWIZZLE_128B, updated in place; bf16 operand: one [128 x 32]
-// box with 64-byte rows, SWIZZLE_64B), each buffer served by its own group of 4 epilogue warps (one per TMEM lane
+// EPI_RESID moves its 128 x 256 tile through shared memory in sixteen sub-steps of 16 columns over four 12 KB buffers
+// (fp32 residual: one [128 x 16] box with 64-byte rows, SWIZZLE_64B, updated in place; 16-bit operand: one [128 x 16]
+// box with 32-byte rows, SWIZZLE_32B), each buffer served by its own group of 4 epilogue warps (one per TMEM lane
 // quarter): while one buffer is computed on, the others' stores drain and their next residual pieces load.
+// Round 2: the sub-steps were halved (32 -> 16 columns) to pay for a FIFTH ring stage — the residual GEMMs stream the
+// fp32 tile in and out beside the operands, the loads take longer to land, and with four stages the MMA warp ran dry
+// (3 stages: down +18 %, proj +8 %; profiles/r02l_summary.md).
 // History (profiles/): whole-tile buffers with 128 x 160 tiles left a 4-stage ring of short stages and a serial
 // load -> compute -> store chain (tensor pipe 29 % / 43 %); 256-wide tiles keep the operand traffic per FLOP of the
 // gate|up GEMM, small buffers keep a 4-stage ring of 32 KB stages.
-constexpr int kSubX = 128 * 128;      // [128 rows x 32 fp32]
-constexpr int kSubXb = 128 * 64;      // [128 rows x 32 bf16]
-constexpr int kSubBytes = kSubX + kSubXb;
+// Two shapes of the same epilogue (internal id EPI_RESID_DEEP = EPI_RESID with the deep ring):
+//   EPI_RESID       32-column sub-steps (8 per tile; 128-byte fp32 rows / 64-byte 16-bit rows), 4-stage ring — for short
+//                   K (proj, K = 1280: 20 k-blocks per tile), where the epilogue's residual traffic is the long pole and
+//                   wide TMA boxes serve it best;
+//   EPI_RESID_DEEP  16-column sub-steps (16 per tile; 64- / 32-byte rows), 5-stage ring — for long K (down, K = 3456),
+//                   where the MMA warp running dry on a 4-stage ring was the long pole.
+// A/B in one session (profiles/r02l_summary.md): proj 80.3 us with 32-column sub-steps vs 90.6 with 16; down 149.7 vs 136.1.
+constexpr int EPI_RESID_DEEP = 100;
+__host__ __device__ constexpr int sub_cols(int epi) { return epi == EPI_RESID_DEEP ? 16 : 32; }      // columns per sub-step
+__host__ __device__ constexpr int sub_steps(int epi) { return 256 / sub_cols(epi); }                  // sub-steps per 256-column tile
+__host__ __device__ constexpr int sub_x_bytes(int epi) { return 128 * sub_cols(epi) * 4; }            // [128 rows x cols fp32], swizzle span = row bytes
+__host__ __device__ constexpr int sub_bytes(int epi) { return sub_x_bytes(epi) + 128 * sub_cols(epi) * 2; }   // + [128 rows x cols 16-bit]
 constexpr int kResidBufs = 4;
+template <int EPI> constexpr bool is_resid = EPI == EPI_RESID || EPI == EPI_RESID_DEEP;
+// 16-byte chunk swizzle of a row of RB bytes as TMA SWIZZLE_{128,64,32}B lays it out
+template <int RB>
+__device__ __forceinline__ int swz(int row) {
+  return RB == 128 ? (row & 7) : RB == 64 ? ((row >> 1) & 3) : ((row >> 2) & 1);
+}
 template <int V>
 struct Cfg2<EPI_RESID, V> {
   static constexpr int BN = 256, groups = 4, stages = 4;
-  static constexpr int out_bytes = kResidBufs * kSubBytes;
+  static constexpr int out_bytes = kResidBufs * sub_bytes(EPI_RESID);
   static constexpr int aux_bytes = 4 * 128 * 4;          // per warp group partial sums of squares
+};
+template <int V>
+struct Cfg2<EPI_RESID_DEEP, V> {
+  static constexpr int BN = 256, groups = 4, stages = 5;
+  static constexpr int out_bytes = kResidBufs * sub_bytes(EPI_RESID_DEEP);
+  static constexpr int aux_bytes = 4 * 128 * 4;
 };
 
 template <int EPI, int V>
@@ -157,7 +181,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tm0);
-    if constexpr (EPI == EPI_RESID) tma_prefetch_desc(&tm1);
+    if constexpr (is_resid<EPI>) tma_prefetch_desc(&tm1);
     for (int s = 0; s < C::stages; ++s) {
       mbar_init(&full_bar[s], 1);    // leader's: its own expect_tx arrive; both CTAs' bytes complete on it
       mbar_init(&empty_bar[s], 1);   // multicast tcgen05.commit arrives once in each CTA
@@ -168,7 +192,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_init(&out_free[s], 1);
     }
     for (int s = 0; s < 4; ++s) {
-      mbar_init(&store_ready[s], EPI == EPI_RESID ? E / kResidBufs : E);
+      mbar_init(&store_ready[s], is_resid<EPI> ? E / kResidBufs : E);
       mbar_init(&aux_full[s], 1);
     }
     fence_mbar_init();
@@ -242,18 +266,19 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // the bulk copies and owns their bulk groups.
     const bool issuer = elect_one();
     uint32_t local = 0;
-    if constexpr (EPI == EPI_RESID) {
-      // Sub-step st = 8 * (tile ordinal) + k covers tile columns [32k, 32k + 32) and uses buffer k & 3.  Per buffer:
+    if constexpr (is_resid<EPI>) {
+      constexpr int kSubSteps = sub_steps(EPI), kSubCols = sub_cols(EPI), kSubX = sub_x_bytes(EPI), kSubBytes = sub_bytes(EPI);
+      // Sub-step st = steps * (tile ordinal) + k covers tile columns [cols * k, +cols) and uses buffer k & 3.  Per buffer:
       //   load residual piece -> epilogue (in place) -> store x, xb -> stores have read the buffer -> load its next piece.
       constexpr int NB = kResidBufs;
       float* red = reinterpret_cast<float*>(aux_base);
       const int n_local = tile_begin < tile_end ? (tile_end - tile_begin + tile_step - 1) / tile_step : 0;
-      const int n_sub = 8 * n_local;
+      const int n_sub = kSubSteps * n_local;
       auto coords = [&](int st, int& m0, int& n0, int& n_blk) {
-        const int tile = tile_begin + (st >> 3) * tile_step;
+        const int tile = tile_begin + (st / kSubSteps) * tile_step;
         m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
         n_blk = tile % num_n;
-        n0 = n_blk * BN + (st & 7) * 32;
+        n0 = n_blk * BN + (st % kSubSteps) * kSubCols;
       };
       auto load_x = [&](int st) {   // fp32 residual piece of sub-step st -> its buffer
         int m0, n0, n_blk;
@@ -275,7 +300,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tma_store_2d(&tm1, xb + kSubX, n0, m0);
           tma_store_commit();
         }
-        if ((st & 7) == 7) {
+        if (st % kSubSteps == kSubSteps - 1) {
           // sum of squares of the new residual rows over this tile's 256 columns: one value per (row, column block),
           // part-major [N/256][M] so producers and consumers both touch it coalesced; fixed order -> deterministic
 #pragma unroll
@@ -391,38 +416,40 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int r = m0 + row;
       const bool valid = r < p.M;
 
-      if constexpr (EPI == EPI_RESID) {
-        // warp group g = cg (one warp per TMEM lane quarter) owns buffer g and the sub-steps k = g, g + 4 of every
-        // tile: 32 columns per sub-step, thread = row
+      if constexpr (is_resid<EPI>) {
+        constexpr int kSubSteps = sub_steps(EPI), kSubCols = sub_cols(EPI), kSubX = sub_x_bytes(EPI), kSubBytes = sub_bytes(EPI);
+        constexpr int XR = kSubCols * 4, BR = kSubCols * 2;   // bytes per fp32 / 16-bit row of a sub-step box
+        // (one warp per TMEM lane quarter) owns buffer g and the sub-steps k = g, g + 4, ... of every tile; thread = row
         float* red = reinterpret_cast<float*>(aux_base);
         const int g = cg;
         uint8_t* buf = out_base + g * kSubBytes;
-        uint8_t* xrow = buf + row * 128;               // 8 chunks of 16 bytes, chunk index XOR (row & 7)
-        uint8_t* xbrow = buf + kSubX + row * 64;        // 4 chunks of 16 bytes, chunk index XOR ((row >> 1) & 3)
-        const int sx = row & 7, sb = (row >> 1) & 3;
+        uint8_t* xrow = buf + row * XR;                // 16-byte chunks, chunk index XOR swz<row bytes>(row)
+        uint8_t* xbrow = buf + kSubX + row * BR;
+        const int sx = swz<XR>(row), sb = swz<BR>(row);
+        constexpr int kPer = kSubSteps / kResidBufs;     // sub-steps of a tile per warp group
         float ss = 0.f;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int col = (g + 4 * i) * 32;
-          mbar_wait(&aux_full[g], (2 * local + i) & 1u);   // residual piece landed (the buffer's previous stores have drained)
+        for (int i = 0; i < kPer; ++i) {
+          const int col = (g + kResidBufs * i) * kSubCols;
+          mbar_wait(&aux_full[g], (kPer * local + i) & 1u);   // residual piece landed (the buffer's previous stores have drained)
           if (i == 0) {
             mbar_wait_relaxed(&acc_full[as], use & 1u);
             tc_fence_after();
           }
-          uint32_t v[32];
-          tmem_ld32(taddr + col, v);
+          uint32_t v[kSubCols];
+          if constexpr (kSubCols == 32) tmem_ld32(taddr + col, v); else tmem_ld16(taddr + col, v);
           tmem_ld_wait();
-          if (i == 1) {   // all of this warp's TMEM reads of the tile are complete
+          if (i == kPer - 1) {   // all of this warp's TMEM reads of the tile are complete
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
               if (leader) mbar_arrive(&acc_empty[as]); else mbar_arrive_cluster(acc_empty_leader + as * 8);
             }
           }
-          uint32_t pk[16];
+          uint32_t pk[kSubCols / 2];
           const float ss_before = ss;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
+          for (int j = 0; j < kSubCols / 4; ++j) {
             float4* xp = reinterpret_cast<float4*>(xrow + ((j ^ sx) << 4));
             const float4 xo = *xp;
             const float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + col + 4 * j));
@@ -443,15 +470,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (p.sat != nullptr && !((ss - ss_before) * p.sat_wmax2 < 4.29e9f)) {
               bool hit = false;
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
+              for (int j = 0; j < kSubCols / 2; ++j)
                 hit |= (pk[j] & 0x7fffu) >= 0x7bffu || ((pk[j] >> 16) & 0x7fffu) >= 0x7bffu;
               if (hit) atomicAdd(p.sat, 1u);
             }
           }
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
+          for (int j = 0; j < kSubCols / 8; ++j)
             *reinterpret_cast<uint4*>(xbrow + ((j ^ sb) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-          if (i == 1) red[g * 128 + row] = ss;
+          if (i == kPer - 1) red[g * 128 + row] = ss;
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(&store_ready[g]);
@@ -689,7 +716,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (leader) mbar_arrive(&acc_empty[as]); else mbar_arrive_cluster(acc_empty_leader + as * 8);
         }
       }
-      if constexpr (EPI != EPI_RESID) {
+      if constexpr (!is_resid<EPI>) {
         // this warp's part of the tile is in shared memory: publish it to the async proxy, tell the store warp
         fence_proxy_async();
         __syncwarp();
@@ -720,9 +747,10 @@ cudaError_t launch2(const GemmArgs& a, int num_sms, cudaStream_t stream, const c
     ok = ok && encode(&tm0, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.out_bf16, a.N, a.M, a.ld_out * 2, 40, BM, false);
     tm1 = tm0;
     tm2 = tm0;
-  } else if (EPI == EPI_RESID) {
-    ok = ok && tma_encode_2d_swz(&tm0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a.x, a.N, a.M, a.ldx * 4, 32, BM, 128) &&
-         tma_encode_2d_swz(&tm1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.out_bf16, a.N, a.M, a.ld_out * 2, 32, BM, 64);
+  } else if (is_resid<EPI>) {
+    constexpr int SC = sub_cols(EPI);
+    ok = ok && tma_encode_2d_swz(&tm0, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, a.x, a.N, a.M, a.ldx * 4, SC, BM, SC * 4) &&
+         tma_encode_2d_swz(&tm1, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.out_bf16, a.N, a.M, a.ld_out * 2, SC, BM, SC * 2);
     tm2 = tm1;
   } else if (EPI == EPI_MROPE) {
     ok = ok && encode(&tm0, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, a.out_bf16, a.N, a.M, a.ld_out * 2, 64, BM, true);
@@ -766,7 +794,7 @@ cudaError_t launch2(const GemmArgs& a, int num_sms, cudaStream_t stream, const c
     max_clusters = n < num_sms / 2 ? n : num_sms / 2;
     // experiments only (profiles/README.md): cap the number of co-resident CTA pairs, e.g. to see whether a launch is
     // bound by the SMs it occupies or by what all of them share (L2)
-    const char* cap = getenv(EPI == EPI_RESID ? "VR2_GEMM2_MAX_CLUSTERS_RESID" : "VR2_GEMM2_MAX_CLUSTERS");
+    const char* cap = getenv(is_resid<EPI> ? "VR2_GEMM2_MAX_CLUSTERS_RESID" : "VR2_GEMM2_MAX_CLUSTERS");
     if (cap != nullptr) {
       const int c = atoi(cap);
       if (c > 0 && c < max_clusters) max_clusters = c;
@@ -785,6 +813,8 @@ cudaError_t launch2(const GemmArgs& a, int num_sms, cudaStream_t stream, const c
 }
 
 }  // namespace
+
+constexpr int kResidDeepK = 2048;
 
 bool gemm2_supports(const GemmArgs& a) {
   if (a.A_lo != nullptr || a.row_map != nullptr) return false;
@@ -807,7 +837,11 @@ cudaError_t gemm2_launch(const GemmArgs& a_in, int num_sms, cudaStream_t stream,
   const bool f16 = (a.flags & GEMM_OUT_F16) != 0;
   switch (a.epilogue) {
     case EPI_QKV: return f16 ? launch2<EPI_QKV, 1>(a, num_sms, stream, err) : launch2<EPI_QKV, 0>(a, num_sms, stream, err);
-    case EPI_RESID: return f16 ? launch2<EPI_RESID, 1>(a, num_sms, stream, err) : launch2<EPI_RESID, 0>(a, num_sms, stream, err);
+    case EPI_RESID:
+      // long K: the deep-ring shape (16-column sub-steps, 5 stages); short K: wide sub-steps, 4 stages
+      if (a.K >= kResidDeepK && !getenv("VR2_RESID_WIDE"))
+        return f16 ? launch2<EPI_RESID_DEEP, 1>(a, num_sms, stream, err) : launch2<EPI_RESID_DEEP, 0>(a, num_sms, stream, err);
+      return f16 ? launch2<EPI_RESID, 1>(a, num_sms, stream, err) : launch2<EPI_RESID, 0>(a, num_sms, stream, err);
     case EPI_SWIGLU: return f16 ? launch2<EPI_SWIGLU, 1>(a, num_sms, stream, err) : launch2<EPI_SWIGLU, 0>(a, num_sms, stream, err);
     case EPI_LOGPROB: return launch2<EPI_LOGPROB, 0>(a, num_sms, stream, err);
     case EPI_MROPE: return launch2<EPI_MROPE, 0>(a, num_sms, stream, err);
