@@ -173,3 +173,14 @@ def test_forward_multi_stores_every_destination():
                 assert torch.equal(b[lo:lo + n // 4], want), (grid, n_dst)
                 assert (b[:lo] == 7).all() and (b[lo + n // 4:] == 7).all()
     assert tower.saturation_count() == 0
+    # every precision the bench cycles through at N > 1 (`modes`) reaches the same store
+    grid = [[2, 8, 12], [1, 4, 6]]
+    n = sum(t * h * ww for t, h, ww in grid)
+    x = torch.randn(n, 1176, generator=torch.Generator().manual_seed(73)).to(torch.bfloat16).cuda()
+    for prec in ("bf16", "split", "auto"):
+        tower.set_precision(prec)
+        want = tower(x, grid)
+        bufs = [torch.zeros((n // 4, 3584), dtype=torch.bfloat16, device="cuda") for _ in range(2)]
+        tower.forward_multi(x, grid, [b.data_ptr() for b in bufs])
+        torch.cuda.synchronize()
+        assert all(torch.equal(b, want) for b in bufs), prec

@@ -105,7 +105,10 @@ for o in outs:
         if s.patch_hi > s.patch_lo:
             alone = tower(x[s.patch_lo:s.patch_hi], [list(r) for r in s.grid])
             assert torch.equal(o[s.token_lo:s.token_hi], alone), (rank, s)
-    assert (o.float() - whole.float()).abs().max().item() < 2e-2
+    # vs the unsharded forward: a slice's rows fall into different 128-row key blocks there (another summation order), and
+    # both results are rounded to bf16 — one bf16 ulp of an output of magnitude 4..8 is 0.031
+    assert (o.float() - whole.float()).abs().max().item() < 4e-2
+    assert torch.nn.functional.cosine_similarity(o.float().flatten(), whole.float().flatten(), dim=0).item() > 0.99999
 torch.cuda.synchronize()
 dist.barrier()
 if rank == 0:

@@ -75,12 +75,13 @@ constexpr int kMultiTileBytes = BM * kMultiRowBytes;
 
 template <int BN, int EPI, bool SPLIT>
 __host__ __device__ constexpr int stages_of() {
-  return EPI == EPI_STORE_MULTI ? 3 : Cfg<BN, SPLIT>::stages;
+  // the split operand's stages are 64 KB (A_hi | A_lo | W): two of them beside the tile (the fallback precision)
+  return EPI == EPI_STORE_MULTI ? (SPLIT ? 2 : 3) : Cfg<BN, SPLIT>::stages;
 }
 template <int BN, int EPI, bool SPLIT>
 __host__ __device__ constexpr int smem_of() {
   using C = Cfg<BN, SPLIT>;
-  return EPI == EPI_STORE_MULTI ? 3 * C::stage_bytes + C::bar_bytes + kMultiTileBytes + 1024 : C::smem_bytes;
+  return EPI == EPI_STORE_MULTI ? stages_of<BN, EPI, SPLIT>() * C::stage_bytes + C::bar_bytes + kMultiTileBytes + 1024 : C::smem_bytes;
 }
 
 // Per-warp staging tile that turns thread-per-row register data into row-contiguous global
@@ -788,16 +789,16 @@ cudaError_t gemm_launch(const GemmArgs& a_in, int num_sms, cudaStream_t stream, 
       *err = "gemm: A_lo must be 16-byte aligned for TMA";
       return cudaErrorInvalidValue;
     }
-    if (a.epilogue != EPI_STORE && a.out_lo == nullptr) {
+    if (a.epilogue != EPI_STORE && a.epilogue != EPI_STORE_MULTI && a.out_lo == nullptr) {
       *err = "gemm: split (A_hi + A_lo) GEMM needs out_lo for this epilogue";
       return cudaErrorInvalidValue;
     }
   }
   switch (a.epilogue) {
     case EPI_STORE_MULTI:
-      if (a.n_multi < 1 || a.n_multi > kMaxMultiOut || a.A_lo != nullptr || (a.flags & (GEMM_OUT_F32 | GEMM_OUT_F16 | GEMM_GELU)) ||
+      if (a.n_multi < 1 || a.n_multi > kMaxMultiOut || (a.flags & (GEMM_OUT_F32 | GEMM_OUT_F16 | GEMM_GELU)) ||
           a.N % 8 != 0 || (a.ld_out * 2) % 16 != 0) {
-        *err = "gemm: EPI_STORE_MULTI takes 1..8 bf16 destinations, N % 8 == 0, no split operand / GELU / fp32 output";
+        *err = "gemm: EPI_STORE_MULTI takes 1..8 bf16 destinations, N % 8 == 0, no GELU / fp32 output";
         return cudaErrorInvalidValue;
       }
       for (int d = 0; d < a.n_multi; ++d)
@@ -805,7 +806,7 @@ cudaError_t gemm_launch(const GemmArgs& a_in, int num_sms, cudaStream_t stream, 
           *err = "gemm: EPI_STORE_MULTI destinations must be non-null and 16-byte aligned";
           return cudaErrorInvalidValue;
         }
-      return launch<256, EPI_STORE_MULTI, false>(a, num_sms, stream, err);
+      return launch_any<256, EPI_STORE_MULTI>(a, num_sms, stream, err);
     case EPI_STORE:
       if ((a.flags & GEMM_OUT_F32) ? a.out_f32 == nullptr : a.out_bf16 == nullptr) {
         *err = "gemm: missing output";
