@@ -64,6 +64,43 @@ def test_attention_varlen_matches_fp32(lens):
     assert err < 2e-2, err  # P and the output are rounded to bf16
 
 
+@pytest.mark.parametrize("kernel", ["tile", "pipe"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("lens,scale", [([64] * 6, 1.0), ([4, 16, 64, 32, 8, 48, 12], 1.0), ([1024] * 3, 1.0), ([1008, 720], 1.0),
+                                        ([100, 1, 63, 65, 129], 1.0), ([2048, 300, 1024, 7], 1.0), ([196, 196, 784, 128], 1.0),
+                                        ([1024, 1024], 3.0), ([640], 1.0), ([128, 129, 127], 1.0)])
+def test_attention_kernels(kernel, dtype, lens, scale, monkeypatch):
+    """Both schedules (VR2_ATTN_KERNEL: the tile kernel of attention2.cu, the pipelined kernel of attention4.cu) on
+    aligned, ragged and long segments, odd tile counts, and scores whose running maximum keeps growing (scale 3: the
+    lazily raised reference maximum has to rescale O in TMEM)."""
+    from video_r2_b200 import ops
+    monkeypatch.setenv("VR2_ATTN_KERNEL", kernel)
+    heads = 16
+    cu = [0]
+    for L in lens:
+        cu.append(cu[-1] + L)
+    g = torch.Generator().manual_seed(17)
+    qkv = (torch.randn(cu[-1], 3 * heads * 80, generator=g) * scale).to(dtype).cuda()
+    out = ops.attention(qkv, cu, heads)
+    ref = _attn_ref(qkv, cu, heads)
+    err = (out.float() - ref).abs().max().item()
+    assert err < (2.5e-2 if dtype == torch.bfloat16 else 4e-3) * scale, (kernel, dtype, lens, err)
+
+
+def test_attention_pipe_equals_tile_rows(monkeypatch):
+    """A slice encoded alone and inside a batch: the pipelined kernel's result for a row does not depend on what else
+    is in the launch as long as the row's key blocks start at the same offsets (segments that start on 128-row tiles)."""
+    from video_r2_b200 import ops
+    monkeypatch.setenv("VR2_ATTN_KERNEL", "pipe")
+    heads = 16
+    g = torch.Generator().manual_seed(19)
+    qkv = torch.randn(3 * 1024, 3 * heads * 80, generator=g).to(torch.float16).cuda()
+    whole = ops.attention(qkv, [0, 1024, 2048, 3072], heads)
+    for i in range(3):
+        alone = ops.attention(qkv[i * 1024:(i + 1) * 1024].contiguous(), [0, 1024], heads)
+        assert torch.equal(alone, whole[i * 1024:(i + 1) * 1024])
+
+
 # ------------------------------------------------------------------ "split" precision (hi + lo bf16 operands)
 @pytest.mark.parametrize("M,N,K", [(200, 288, 1176), (1000, 1280, 1280), (4096, 1280, 3456), (513, 3584, 5120)])
 def test_linear_split_matches_fp32(M, N, K):
