@@ -68,7 +68,8 @@ def test_attention_varlen_matches_fp32(lens):
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("lens,scale", [([64] * 6, 1.0), ([4, 16, 64, 32, 8, 48, 12], 1.0), ([1024] * 3, 1.0), ([1008, 720], 1.0),
                                         ([100, 1, 63, 65, 129], 1.0), ([2048, 300, 1024, 7], 1.0), ([196, 196, 784, 128], 1.0),
-                                        ([1024, 1024], 3.0), ([640], 1.0), ([128, 129, 127], 1.0)])
+                                        ([1024, 1024], 3.0), ([640], 1.0), ([128, 129, 127], 1.0), ([64] * 300, 1.0), ([128] * 37, 2.0),
+                                        ([16, 48, 64, 32, 32, 64, 128, 64, 60, 4] * 31, 1.0), ([32] * 9, 1.0)])
 def test_attention_kernels(kernel, dtype, lens, scale, monkeypatch):
     """Both schedules (VR2_ATTN_KERNEL: the tile kernel of attention2.cu, the pipelined kernel of attention4.cu) on
     aligned, ragged and long segments, odd tile counts, and scores whose running maximum keeps growing (scale 3: the

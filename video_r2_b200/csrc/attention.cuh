@@ -21,8 +21,11 @@ cudaError_t attention_tc_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, co
 cudaError_t attention_pipe_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, const int2* seg, int n_rows, int num_heads,
                                   int64_t ld_qkv, int64_t ld_out, int num_sms, cudaStream_t stream, bool f16 = false);
 
-// Which of the two serves a launch: VR2_ATTN_KERNEL=tile|pipe forces one (A/B runs, tests); otherwise the pipelined
-// kernel takes the launches whose segments are longer than two key blocks of the tile kernel.
-bool attention_use_pipe(bool long_segments);
+// Which kernel serves a launch.  VR2_ATTN_KERNEL=tile|pipe forces one (A/B runs, tests); otherwise launches with long
+// segments (the full-attention layers) take the pipelined kernel, the window layers the tile kernel.
+enum AttnKind { ATTN_TILE = 0, ATTN_PIPE = 1 };
+AttnKind attention_kind(bool long_segments);
+cudaError_t attention_launch(AttnKind kind, const __nv_bfloat16* qkv, __nv_bfloat16* out, const int2* seg, int n_rows,
+                             int num_heads, int64_t ld_qkv, int64_t ld_out, int num_sms, cudaStream_t stream, bool f16);
 
 }  // namespace vr2

@@ -97,17 +97,10 @@ __host__ __device__ constexpr uint32_t idesc16(int m, int n, bool b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (b_mn_major ? (1u << 16) : 0u) | (static_cast<uint32_t>(n >> 3) << 17) |
          (static_cast<uint32_t>(m >> 4) << 24);
 }
-#ifndef ATTN_EXP
-#define ATTN_EXP 0   // timing experiments only (results are wrong): 1 no MUFU, 2 no N=16 P V MMAs, 3 no P V, 4 no S MMAs, 5 no P stores
-#endif
 __device__ __forceinline__ float ex2_approx(float x) {
-#if ATTN_EXP == 1
-  return x * 0.001f;
-#else
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
-#endif
 }
 
 // key blocks of one work item: block j covers rows [lo0 + 64 j, +64); stream x takes part in blocks [jb[x], je[x])
@@ -222,12 +215,7 @@ attn_pipe_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constan
         mbar_wait(&kv_empty[s], ph ^ 1u);
         uint8_t* kb = smem + OFF_KV + s * KV_STAGE;
         const int row = cur.lo0 + j * TK;
-#if ATTN_EXP == 8
-        if (issuer) mbar_arrive(&kv_full[s]);
-        if (false) {
-#else
         if (issuer) {
-#endif
           mbar_expect_tx(&kv_full[s], KV_STAGE);
           tma_load_2d(kb, &tmK64, &kv_full[s], hidden + head * HD, row);
           tma_load_2d(kb + K64_BYTES, &tmK16, &kv_full[s], hidden + head * HD + 64, row);
@@ -278,12 +266,10 @@ attn_pipe_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constan
           const uint32_t bs = (g0 + static_cast<uint32_t>(t)) & 1u;
           const uint32_t d = t_s + bs * TK;
           if (issuer) {
-#if ATTN_EXP != 4
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_bf16(d, umma_desc_sw128(q_addr + k * 32), umma_desc_sw128(k_addr + k * 32), id_s, k != 0 ? 1u : 0u);
             umma_bf16(d, desc_k_sw32(q_addr + Q64_BYTES), desc_k_sw32(k_addr + K64_BYTES), id_s, 1u);
-#endif
             umma_commit(&s_full[x * 2 + bs]);
             if (t == n - 1) umma_commit(&q_empty[x]);   // the item's last S: Q is free once it retires
           }
@@ -304,12 +290,8 @@ attn_pipe_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constan
 #pragma unroll
             for (int kk = 0; kk < TK / 16; ++kk) {
               const uint64_t da = umma_desc_sw128(p_addr + kk * 32);
-#if ATTN_EXP != 3
               umma_bf16(t_o, da, desc_mn_sw128(v_addr + kk * 2048), id_o64, (kk != 0 || t != 0) ? 1u : 0u);
-#if ATTN_EXP != 2
               umma_bf16(t_o + 64, da, desc_mn_sw32(v_addr + K64_BYTES + kk * 512), id_o16, (kk != 0 || t != 0) ? 1u : 0u);
-#endif
-#endif
             }
             umma_commit(&kv_empty[s]);          // K (read by S(t) earlier) and V of this block: this stream is done with them
             umma_commit(&pv_done[x * 2 + b]);
@@ -389,18 +371,9 @@ attn_pipe_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constan
             // reference by more than kTau (rare after the first block) is the block redone.  Barrier tests are issued
             // early and consumed late so their round trips hide behind the exponentials.
             uint32_t v[TK];
-#if ATTN_EXP == 6 || ATTN_EXP == 7
-#pragma unroll
-            for (int i = 0; i < TK; ++i) v[i] = __float_as_uint(static_cast<float>((tid * 64 + i + t) & 1023) * 1e-3f);
-#else
             tmem_ld32(t_s + b * TK, v);
             tmem_ld32(t_s + b * TK + 32, v + 32);
             tmem_ld_wait();
-#endif
-#if ATTN_EXP == 7
-            float rs0 = 0.f, rs1 = 0.f;
-            if (v[5] == 0x12345u) {
-#endif
             if (t == 0) {
               float m0 = __uint_as_float(v[0]), m1 = __uint_as_float(v[1]), m2 = __uint_as_float(v[2]), m3 = __uint_as_float(v[3]);
 #pragma unroll
@@ -414,11 +387,7 @@ attn_pipe_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constan
             }
             // the P V that read this probability buffer two blocks ago (or in the previous item) has retired?
             const bool pv_ok = g < 2u || mbar_try_wait(&pv_done[x * 2 + b], ph ^ 1u);
-#if ATTN_EXP == 7
-            float mx;
-#else
             float rs0, rs1, mx;
-#endif
             bool p_free = pv_ok;
             auto exps = [&]() {   // probabilities of the block against m_ref -> shared memory; row sum, block maximum
               const float m_scaled = m_ref * scale_log2;   // -inf reference (no valid key so far): redone below
@@ -443,9 +412,6 @@ attn_pipe_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constan
                   mbar_wait(&pv_done[x * 2 + b], ph ^ 1u);
                   p_free = true;
                 }
-#if ATTN_EXP == 5
-                if (pk[0] == 0x12345u)
-#endif
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                   *reinterpret_cast<uint4*>(prow + (((4 * h + q) ^ (tid & 7)) << 4)) =
@@ -463,10 +429,6 @@ attn_pipe_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constan
             }
             // early test of the next block's score tile (issued two blocks ahead of us by the MMA warp)
             s_ok = t + 1 < n && mbar_try_wait(&s_full[x * 2 + (b ^ 1u)], ((g + 1u) >> 1) & 1u);
-#if ATTN_EXP == 7
-            }
-            if (g >= 2u) mbar_wait(&pv_done[x * 2 + b], ph ^ 1u);
-#endif
             l_run += rs0 + rs1;
           } else {
             // ---- a segment boundary cuts the block for some row of the warp (ragged batches, the ends of a slice)
@@ -574,11 +536,19 @@ attn_pipe_kernel(const __grid_constant__ CUtensorMap tmQ64, const __grid_constan
 
 }  // namespace
 
-bool attention_use_pipe(bool long_segments) {
+AttnKind attention_kind(bool long_segments) {
   const char* e = getenv("VR2_ATTN_KERNEL");
-  if (e != nullptr && strcmp(e, "tile") == 0) return false;
-  if (e != nullptr && strcmp(e, "pipe") == 0) return true;
-  return long_segments;
+  if (e != nullptr && strcmp(e, "tile") == 0) return ATTN_TILE;
+  if (e != nullptr && strcmp(e, "pipe") == 0) return ATTN_PIPE;
+  return long_segments ? ATTN_PIPE : ATTN_TILE;
+}
+
+cudaError_t attention_launch(AttnKind kind, const __nv_bfloat16* qkv, __nv_bfloat16* out, const int2* seg, int n_rows,
+                             int num_heads, int64_t ld_qkv, int64_t ld_out, int num_sms, cudaStream_t stream, bool f16) {
+  switch (kind) {
+    case ATTN_PIPE: return attention_pipe_launch(qkv, out, seg, n_rows, num_heads, ld_qkv, ld_out, num_sms, stream, f16);
+    default: return attention_tc_launch(qkv, out, seg, n_rows, num_heads, ld_qkv, ld_out, num_sms, stream, f16);
+  }
 }
 
 cudaError_t attention_pipe_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, const int2* seg, int n_rows, int num_heads,

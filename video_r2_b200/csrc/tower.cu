@@ -524,12 +524,9 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
       if (split)   // hi + lo operands: 3 tcgen05 products per contraction (attention3.cu)
         VR2_CUDA(attention_split_launch(w.qkv, w.qkv_lo, w.att, w.att_lo, full ? plan->seg_full : plan->seg_window,
                                         static_cast<int>(N), t->cfg.num_heads, 3 * h, h, t->num_sms, s));
-      else if (attention_use_pipe(full))
-        VR2_CUDA(attention_pipe_launch(w.qkv, w.att, full ? plan->seg_full : plan->seg_window, static_cast<int>(N),
-                                       t->cfg.num_heads, 3 * h, h, t->num_sms, s, f16));
       else
-        VR2_CUDA(attention_tc_launch(w.qkv, w.att, full ? plan->seg_full : plan->seg_window, static_cast<int>(N),
-                                     t->cfg.num_heads, 3 * h, h, t->num_sms, s, f16));
+        VR2_CUDA(attention_launch(attention_kind(full), w.qkv, w.att, full ? plan->seg_full : plan->seg_window, static_cast<int>(N), t->cfg.num_heads,
+                                  3 * h, h, t->num_sms, s, f16));
     }
     {
       GemmArgs a{};
@@ -850,12 +847,10 @@ static int op_attention_impl(const void* qkv, const void* qkv_lo, void* out, voi
     if (e == cudaSuccess) {
       int longest = 0;
       for (int i = 0; i < n_seq; ++i) longest = cu[i + 1] - cu[i] > longest ? cu[i + 1] - cu[i] : longest;
-      if (qkv_lo == nullptr && attention_use_pipe(longest > 256))
-        e = attention_pipe_launch(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out),
-                                  static_cast<const int2*>(d), n_rows, num_heads, 3 * num_heads * 80, num_heads * 80, sms, s, f16);
-      else if (qkv_lo == nullptr)
-        e = attention_tc_launch(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out),
-                                static_cast<const int2*>(d), n_rows, num_heads, 3 * num_heads * 80, num_heads * 80, sms, s, f16);
+      if (qkv_lo == nullptr)
+        e = attention_launch(attention_kind(longest > 256), static_cast<const __nv_bfloat16*>(qkv),
+                             static_cast<__nv_bfloat16*>(out), static_cast<const int2*>(d), n_rows, num_heads,
+                             3 * num_heads * 80, num_heads * 80, sms, s, f16);
       else
         e = attention_split_launch(static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(qkv_lo),
                                    static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(out_lo),
