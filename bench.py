@@ -244,6 +244,8 @@ def run_vr2(args, rank, local_rank, world):
 
     dev = torch.device(f"cuda:{local_rank}")
     torch.cuda.set_device(dev)
+    # one process per GPU: keep this rank's threads and pinned buffers on the GPU's own NUMA node
+    host_cores = vr2.bind_to_gpu_node(dev) if world > 1 else []
     if world > 1:
         # NCCL prints its version banner on stdout at communicator creation: keep stdout to the one JSON line
         sys.stdout.flush()
@@ -679,6 +681,7 @@ def run_vr2(args, rank, local_rank, world):
             "precision": args.precision,
             "step_tflops": tokens_total * FLOP_PER_TOKEN / (ms_step * 1e-3) / 1e12 / world,
             "gather": gather_how,
+            "host_cores_rank0": (f"{len(host_cores)} cores local to the GPU (NVML affinity)" if host_cores else "not bound"),
         },
         "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic,

@@ -11,12 +11,12 @@ from .rope_index import RopeConfig, get_rope_index
 from .embed import embed_visual_tokens, scatter_rows, token_positions
 from .logprob import lm_logprob
 from .mrope import FusedDecoderQKV, apply_mrope, mrope_table
-from .pipeline import HostPipeline
+from .pipeline import HostPipeline, bind_to_gpu_node
 from .preprocess import patchify, preprocess_video, resize_frames, smart_nframes, smart_resize, video_target_size
 from .tower import Plan, VisionConfig, VisionTower, gather_rows
 
 __all__ = ["LIB_PATH", "Vr2Error", "lib", "RopeConfig", "get_rope_index", "Plan", "VisionConfig", "VisionTower",
-           "gather_rows", "HostPipeline", "patchify", "resize_frames", "preprocess_video", "smart_resize", "smart_nframes", "video_target_size", "apply_mrope", "mrope_table", "FusedDecoderQKV", "lm_logprob", "embed_visual_tokens", "scatter_rows", "token_positions", "install", "uninstall", "refresh"]
+           "gather_rows", "HostPipeline", "bind_to_gpu_node", "patchify", "resize_frames", "preprocess_video", "smart_resize", "smart_nframes", "video_target_size", "apply_mrope", "mrope_table", "FusedDecoderQKV", "lm_logprob", "embed_visual_tokens", "scatter_rows", "token_positions", "install", "uninstall", "refresh"]
 
 
 def install(*args, **kwargs):

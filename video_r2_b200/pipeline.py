@@ -22,6 +22,34 @@ from .preprocess import patchify, resize_frames
 from .rope_index import get_rope_index
 
 
+def bind_to_gpu_node(device) -> list:
+    """Restricts this process to the CPU cores NVML reports as local to `device` (its NUMA node), so that the pinned
+    host buffers allocated afterwards and the threads that feed the copy engines sit next to the GPU's PCIe root.  With
+    one process per GPU on a two-socket host this keeps eight ranks' H2D / D2H traffic off the inter-socket link.
+    Returns the core list it bound to ([] when NVML, the affinity call or a usable mask is unavailable: nothing is
+    changed then).  Call it once per rank before creating a HostPipeline."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        dev = torch.device(device)
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:   # NVML counts physical devices
+            idx = int(vis.split(",")[idx])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cores = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        allowed = sorted(set(cores) & os.sched_getaffinity(0))
+        if not allowed:
+            return []
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return []
+
+
 class HostPipeline:
     _SNAPS = 256   # guard snapshots kept (= batches that may be in flight)
 
