@@ -525,8 +525,8 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
         VR2_CUDA(attention_split_launch(w.qkv, w.qkv_lo, w.att, w.att_lo, full ? plan->seg_full : plan->seg_window,
                                         static_cast<int>(N), t->cfg.num_heads, 3 * h, h, t->num_sms, s));
       else
-        VR2_CUDA(attention_launch(attention_kind(full), w.qkv, w.att, full ? plan->seg_full : plan->seg_window, static_cast<int>(N), t->cfg.num_heads,
-                                  3 * h, h, t->num_sms, s, f16));
+        VR2_CUDA(attention_tc_launch(w.qkv, w.att, full ? plan->seg_full : plan->seg_window, static_cast<int>(N),
+                                     t->cfg.num_heads, 3 * h, h, t->num_sms, s, f16));
     }
     {
       GemmArgs a{};
@@ -845,12 +845,9 @@ static int op_attention_impl(const void* qkv, const void* qkv_lo, void* out, voi
     VR2_CUDA(cudaMalloc(&d, seg.size() * 8));
     e = cudaMemcpyAsync(d, seg.data(), seg.size() * 8, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) {
-      int longest = 0;
-      for (int i = 0; i < n_seq; ++i) longest = cu[i + 1] - cu[i] > longest ? cu[i + 1] - cu[i] : longest;
       if (qkv_lo == nullptr)
-        e = attention_launch(attention_kind(longest > 256), static_cast<const __nv_bfloat16*>(qkv),
-                             static_cast<__nv_bfloat16*>(out), static_cast<const int2*>(d), n_rows, num_heads,
-                             3 * num_heads * 80, num_heads * 80, sms, s, f16);
+        e = attention_tc_launch(static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(out),
+                                static_cast<const int2*>(d), n_rows, num_heads, 3 * num_heads * 80, num_heads * 80, sms, s, f16);
       else
         e = attention_split_launch(static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(qkv_lo),
                                    static_cast<__nv_bfloat16*>(out), static_cast<__nv_bfloat16*>(out_lo),
