@@ -5,7 +5,8 @@ import csv
 import re
 import sys
 
-EPI = {"0": "EPI_STORE (merger fc1/fc2)", "1": "EPI_RESID (patch-embed, proj, down)", "2": "EPI_QKV", "3": "EPI_SWIGLU (gate|up)"}
+EPI = {"0": "EPI_STORE (merger fc1/fc2)", "1": "EPI_RESID (patch-embed, proj, down)", "2": "EPI_QKV", "3": "EPI_SWIGLU (gate|up)",
+       "100": "EPI_RESID deep ring (down)", "4": "EPI_LOGPROB", "5": "EPI_STORE_MULTI", "6": "EPI_MROPE"}
 
 
 def main(path):
