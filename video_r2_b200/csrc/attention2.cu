@@ -109,7 +109,7 @@ template <int F16>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__ CUtensorMap tm16,
                const __grid_constant__ CUtensorMap tmOut, const int2* __restrict__ seg, int n_rows, int num_heads,
-               int hidden, float scale_log2) {
+               int hidden, float scale_log2, int reverse) {
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
 
@@ -126,6 +126,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
   const int lane = threadIdx.x & 31;
   const int n_tiles = (n_rows + TQ - 1) / TQ;
   const int n_items = n_tiles * num_heads;
+  // query tile of an item: ascending, or (reverse) from the last tile down — see GEMM_REVERSE_M in gemm.cuh
+  auto tile_of = [&](int item) { return reverse ? n_tiles - 1 - item / num_heads : item / num_heads; };
 
   if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tm64);
@@ -156,7 +158,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
   // key/value block range of a query tile: from the segment start of its first row to the segment end of its last
   auto kv_range = [&](int item, int& kv_lo, int& nblk) {
     if (item >= n_items) { kv_lo = 0; nblk = 0; return; }
-    const int r0 = (item / num_heads) * TQ;
+    const int r0 = tile_of(item) * TQ;
     const int r1 = min(r0 + TQ, n_rows) - 1;
     kv_lo = seg[r0].x;
     nblk = (seg[r1].y - kv_lo + TK - 1) / TK;
@@ -172,7 +174,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
       const bool issuer = elect_one();
       uint32_t it = 0, pair_no = 0;
       auto load_q = [&](int x, int item) {
-        const int tile = item / num_heads, head = item % num_heads;
+        const int tile = tile_of(item), head = item % num_heads;
         mbar_wait(&q_empty[x], (pair_no & 1u) ^ 1u);     // the stream's previous item's S MMAs have read Q
         uint8_t* q = smem + OFF_Q + x * TILE_BYTES;
         if (issuer) {
@@ -297,7 +299,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
     uint8_t* pbuf = smem + OFF_P + x * P_BYTES;
     uint32_t nblk_done = 0;   // blocks of this stream processed so far (barrier phases)
     for (int item = blockIdx.x + x * gridDim.x; item < n_items; item += 2 * gridDim.x) {
-      const int tile = item / num_heads, head = item % num_heads;
+      const int tile = tile_of(item), head = item % num_heads;
       int kv_lo, nblk;
       kv_range(item, kv_lo, nblk);
       const int r = tile * TQ + tid;
@@ -487,7 +489,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tm64, const __grid_constant__
 }  // namespace
 
 cudaError_t attention_tc_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, const int2* seg, int n_rows, int num_heads,
-                                int64_t ld_qkv, int64_t ld_out, int num_sms, cudaStream_t stream, bool f16) {
+                                int64_t ld_qkv, int64_t ld_out, int num_sms, cudaStream_t stream, bool f16, bool reverse) {
   if (n_rows <= 0) return cudaSuccess;
   const int hidden = num_heads * HD;
   CUtensorMap tm64, tm16, tmOut;
@@ -506,8 +508,8 @@ cudaError_t attention_tc_launch(const __nv_bfloat16* qkv, __nv_bfloat16* out, co
   const int items = ((n_rows + TQ - 1) / TQ) * num_heads;
   const int grid = items < num_sms ? items : num_sms;
   const float scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
-  if (f16) attn_tc_kernel<1><<<grid, kThreads, SMEM_BYTES, stream>>>(tm64, tm16, tmOut, seg, n_rows, num_heads, hidden, scale_log2);
-  else attn_tc_kernel<0><<<grid, kThreads, SMEM_BYTES, stream>>>(tm64, tm16, tmOut, seg, n_rows, num_heads, hidden, scale_log2);
+  if (f16) attn_tc_kernel<1><<<grid, kThreads, SMEM_BYTES, stream>>>(tm64, tm16, tmOut, seg, n_rows, num_heads, hidden, scale_log2, reverse ? 1 : 0);
+  else attn_tc_kernel<0><<<grid, kThreads, SMEM_BYTES, stream>>>(tm64, tm16, tmOut, seg, n_rows, num_heads, hidden, scale_log2, reverse ? 1 : 0);
   return cudaGetLastError();
 }
 

@@ -30,6 +30,8 @@ enum GemmFlags : int {
   GEMM_OUT_F32 = 4,    // EPI_STORE: fp32 output (else bf16)
   GEMM_A_F16 = 8,      // A and W hold fp16 (the f16 activation mode); kind::f16 rejects mixed fp16 x bf16 operands
   GEMM_OUT_F16 = 16,   // the 16-bit output (out_bf16: EPI_STORE / xb / qkv / h) is written as fp16, saturating
+  GEMM_REVERSE_M = 32, // CTA-pair kernel: walk the row blocks from the last one down.  Same tiles, same arithmetic per
+                       // element; a launch that starts where its producer stopped finds those rows in L2 still
 };
 
 struct GemmArgs {

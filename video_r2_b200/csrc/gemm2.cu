@@ -175,6 +175,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int tile_begin = cluster_id;
   const int tile_end = num_tiles;
   const int tile_step = num_clusters;
+  // row block of a tile: ascending, or (GEMM_REVERSE_M) descending — consecutive launches of the tower alternate, so
+  // every launch starts on the rows its producer wrote last (the likeliest to be in L2 still) and ends on the rows its
+  // consumer will start with
+  const int m_flip = (p.flags & GEMM_REVERSE_M) != 0 ? num_pair_m - 1 : -1;
+  auto tile_row = [&](int tile) { return m_flip >= 0 ? m_flip - tile / num_n : tile / num_n; };
 
   constexpr int kProducerWarp = E, kMmaWarp = E + 1, kStoreWarp = E + 2;
   if (warp == kProducerWarp && lane == 0) {
@@ -210,7 +215,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ------------------------------------------------------------ TMA producer (whole warp, one elected lane issues)
     uint32_t it = 0;
     for (int tile = tile_begin; tile < tile_end; tile += tile_step) {
-      const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
+      const int m0 = tile_row(tile) * (2 * BM) + static_cast<int>(rank) * BM;
       const int n0 = (tile % num_n) * BN + static_cast<int>(rank) * L::half_n;
       for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
         const uint32_t s = it % C::stages;
@@ -276,7 +281,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int n_sub = kSubSteps * n_local;
       auto coords = [&](int st, int& m0, int& n0, int& n_blk) {
         const int tile = tile_begin + (st / kSubSteps) * tile_step;
-        m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
+        m0 = tile_row(tile) * (2 * BM) + static_cast<int>(rank) * BM;
         n_blk = tile % num_n;
         n0 = n_blk * BN + (st % kSubSteps) * kSubCols;
       };
@@ -329,7 +334,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                      : "memory");
       }
       for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++local) {
-        const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
+        const int m0 = tile_row(tile) * (2 * BM) + static_cast<int>(rank) * BM;
         const int n0 = (tile % num_n) * BN;
         mbar_wait(&store_ready[0], local & 1u);
         if (issuer) {
@@ -345,7 +350,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       // combine the 4 column groups' (max, sum-exp) per row in a fixed order and write the block's partial,
       // part-major; out_free[parity] tells the epilogue warps the slot may be rewritten
       for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++local) {
-        const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
+        const int m0 = tile_row(tile) * (2 * BM) + static_cast<int>(rank) * BM;
         const int n_blk = tile % num_n;
         mbar_wait(&store_ready[0], local & 1u);
         const float2* red = reinterpret_cast<const float2*>(aux_base) + (local & 1u) * 4 * 128;
@@ -371,7 +376,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     } else if constexpr (EPI == EPI_MROPE) {
       for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++local) {
-        const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
+        const int m0 = tile_row(tile) * (2 * BM) + static_cast<int>(rank) * BM;
         const int n0 = (tile % num_n) * BN;
         mbar_wait(&store_ready[0], local & 1u);
         if (issuer) {
@@ -385,7 +390,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     } else {  // EPI_SWIGLU
       for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++local) {
-        const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
+        const int m0 = tile_row(tile) * (2 * BM) + static_cast<int>(rank) * BM;
         const int n_blk = tile % num_n;
         mbar_wait(&store_ready[0], local & 1u);
         if (issuer) {
@@ -408,7 +413,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint32_t local = 0;
     for (int tile = tile_begin; tile < tile_end; tile += tile_step, ++local) {
       const int n_blk = tile % num_n;
-      const int m0 = (tile / num_n) * (2 * BM) + static_cast<int>(rank) * BM;
+      const int m0 = tile_row(tile) * (2 * BM) + static_cast<int>(rank) * BM;
       const int n0 = n_blk * BN;
       const uint32_t as = local & 1u;
       const uint32_t use = local >> 1;

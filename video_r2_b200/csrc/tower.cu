@@ -15,6 +15,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -464,8 +465,14 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
   int parts = 0;  // sum-of-squares partials per row written by the most recent EPI_RESID launch
   const float eps = t->cfg.rms_norm_eps;
   const char* msg = "";
+  // Consecutive launches walk the rows in opposite directions (GEMM_REVERSE_M / the attention kernel's `reverse`):
+  // every launch then starts on the rows its producer wrote last — the ones still in the 126 MB L2 — instead of on the
+  // rows that were evicted longest ago.  Same tiles and arithmetic either way (VR2_ALTERNATE=0 turns it off for A/B).
+  static const bool alternate = [] { const char* e = getenv("VR2_ALTERNATE"); return e == nullptr || e[0] != '0'; }();
+  int n_launch = 0;
   auto G = [&](GemmArgs& a, int kind, const char* what) -> int {
     ProfScope prof(t, kind, s);
+    if (alternate && (n_launch++ & 1)) a.flags |= GEMM_REVERSE_M;
     const int site = a.epilogue == EPI_QKV ? 1 : a.epilogue == EPI_SWIGLU ? 2 : a.epilogue == EPI_RESID ? 0 : 3;
     a.sat = f16 ? t->sat + site : nullptr;
     if (a.epilogue == EPI_RESID) parts = gemm_resid_parts(a);
@@ -526,7 +533,8 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
                                         static_cast<int>(N), t->cfg.num_heads, 3 * h, h, t->num_sms, s));
       else
         VR2_CUDA(attention_tc_launch(w.qkv, w.att, full ? plan->seg_full : plan->seg_window, static_cast<int>(N),
-                                     t->cfg.num_heads, 3 * h, h, t->num_sms, s, f16));
+                                     t->cfg.num_heads, 3 * h, h, t->num_sms, s, f16, alternate && (n_launch & 1)));
+      ++n_launch;
     }
     {
       GemmArgs a{};
