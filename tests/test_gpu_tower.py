@@ -142,6 +142,25 @@ def test_slice_independence_and_determinism():
     assert torch.equal(a, b) and torch.equal(a, c)
 
 
+@pytest.mark.parametrize("prec", ["f16", "bf16"])
+def test_traversal_order_does_not_change_a_bit(prec, monkeypatch):
+    """Consecutive launches walk the row blocks in opposite directions (GEMM_REVERSE_M / attention `reverse`)
+    so that each starts on the rows its producer left in L2: a scheduling choice — the outputs are the same bits as with
+    every launch ascending (VR2_ALTERNATE=0), on a grid with partial windows and a ragged last tile."""
+    import video_r2_b200 as vr2
+    cfg = T.TowerConfig(depth=4, fullatt_block_indexes=(1, 3))
+    w = T.make_weights(cfg, seed=5)
+    tower = vr2.VisionTower(vr2.VisionConfig(depth=4, fullatt_block_indexes=(1, 3)), w, device="cuda:0", precision=prec)
+    grid = [[3, 26, 18], [2, 32, 32]]
+    n = sum(t * h * ww for t, h, ww in grid)
+    x = torch.randn(n, 1176, generator=torch.Generator().manual_seed(6)).to(torch.bfloat16).cuda()
+    monkeypatch.setenv("VR2_ALTERNATE", "1")
+    a = tower(x, grid, out_dtype=torch.float32).clone()
+    monkeypatch.setenv("VR2_ALTERNATE", "0")
+    b = tower(x, grid, out_dtype=torch.float32).clone()
+    assert torch.equal(a, b)
+
+
 def test_shape_errors_raise_value_error():
     cfg = T.TowerConfig(depth=1, fullatt_block_indexes=(0,))
     tower = _tower(cfg, T.make_weights(cfg, seed=1))

@@ -468,7 +468,8 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
   // Consecutive launches walk the rows in opposite directions (GEMM_REVERSE_M / the attention kernel's `reverse`):
   // every launch then starts on the rows its producer wrote last — the ones still in the 126 MB L2 — instead of on the
   // rows that were evicted longest ago.  Same tiles and arithmetic either way (VR2_ALTERNATE=0 turns it off for A/B).
-  static const bool alternate = [] { const char* e = getenv("VR2_ALTERNATE"); return e == nullptr || e[0] != '0'; }();
+  const char* alt_env = getenv("VR2_ALTERNATE");   // read per forward: tests toggle it
+  const bool alternate = alt_env == nullptr || alt_env[0] != '0';
   int n_launch = 0;
   auto G = [&](GemmArgs& a, int kind, const char* what) -> int {
     ProfScope prof(t, kind, s);
