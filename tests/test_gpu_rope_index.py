@@ -67,6 +67,53 @@ def test_config2_sequence_and_long_batch(int_cast):
         assert torch.equal(pos, rpos) and torch.equal(delta, rdelta)
 
 
+@pytest.mark.parametrize("int_cast", [True, False], ids=["int64cast", "float32mul"])
+@pytest.mark.parametrize("seed", range(12))
+def test_random_batches_bit_exact(seed, int_cast):
+    """Seeded fuzz: batches of 1-6 rows, each with 0-4 vision items (images and videos mixed in any order, text-only
+    rows included), random even grids, random text gaps (also zero: items back to back), left or right padding or no
+    mask, fractional seconds-per-grid as tensor / list / None — position ids and deltas equal the oracle's, bit for bit."""
+    from rope_cases import IMG
+    rng = np.random.default_rng(1000 + seed)
+    B = int(rng.integers(1, 7))
+    rows, img_grids, vid_grids = [], [], []
+    for _ in range(B):
+        items = []
+        for _ in range(int(rng.integers(0, 5))):
+            kind = IMG if rng.random() < 0.4 else VID
+            g = [1 if kind == IMG else int(rng.integers(1, 7)), int(rng.integers(1, 9)) * 2, int(rng.integers(1, 9)) * 2]
+            items.append((kind, g))
+            (img_grids if kind == IMG else vid_grids).append(g)
+        rows.append(build_row(items, rng, lead=int(rng.integers(0, 12)), gap=int(rng.integers(0, 4)), tail=int(rng.integers(0, 9))))
+        if not rows[-1]:
+            rows[-1] = [1234]
+    mode = ["left", "right", "none"][seed % 3]
+    if mode == "none":   # no attention mask: rows must have one length
+        S = max(len(r) for r in rows)
+        rows = [r + rng.integers(1000, 5000, size=S - len(r)).tolist() for r in rows]
+        kw = dict(input_ids=torch.tensor(rows))
+    else:
+        ids, mask = pad_batch(rows, mode)
+        kw = dict(input_ids=ids, attention_mask=mask)
+    if img_grids:
+        kw["image_grid_thw"] = torch.tensor(img_grids)
+    if vid_grids:
+        kw["video_grid_thw"] = torch.tensor(vid_grids)
+        spg = [float(2.0 / rng.choice([2.0, 1.0, 0.7, 0.2133, 3.0, 0.5, 1.7])) for _ in vid_grids]
+        how = seed % 4
+        if how == 0:
+            kw["second_per_grid_ts"] = torch.tensor(spg, dtype=torch.float32)
+        elif how == 1:
+            kw["second_per_grid_ts"] = spg
+        elif how == 2:
+            kw["second_per_grid_ts"] = torch.tensor([float(round(v)) for v in spg], dtype=torch.float32)
+    if not img_grids and not vid_grids and mode == "none":
+        kw["attention_mask"] = torch.ones_like(kw["input_ids"])
+    pos, delta, rpos, rdelta = _run_both(kw, int_cast)
+    assert torch.equal(pos, rpos), (seed, mode)
+    assert torch.equal(delta, rdelta.to(torch.int64)), (seed, mode)
+
+
 # ---- the CUDA kernel against the fixtures of the two live implementations directly (no oracle in between)
 import json
 import os
