@@ -200,6 +200,16 @@ int vr2_tower_forward_multi(vr2_tower* tower, const vr2_plan* plan, const void* 
                             void* const* outs_host, int32_t n_out, void* workspace_dev, size_t workspace_bytes,
                             void* stream);
 
+/* Test hooks (stage-by-stage parity, tests/test_gpu_stages.py).  vr2_tower_set_debug_stop(n): every following forward
+ * returns after n stages — 1 = patch embed, then qkv, attention, proj, gate|up, down of block 0, and so on — leaving the
+ * caller's workspace as that stage wrote it (0 = off, the default).  vr2_tower_workspace_layout: byte offsets of the
+ * workspace buffers for a forward of n_patches rows, offsets[0..6] = x (fp32 [N, hidden], residual stream), xb (16-bit
+ * [N, hidden], x times the next norm weight), qkv (16-bit [N, 3 hidden]), att (16-bit [N, hidden]), h (16-bit [N, *h_ld],
+ * SwiGLU output, columns >= intermediate_size are padding), ssq (fp32 [parts][N] partial sums of x^2, parts =
+ * hidden / 256 from the CTA-pair kernel), pix (pixel staging).  All in WINDOW order (vr2_plan_export). */
+int vr2_tower_set_debug_stop(vr2_tower* tower, int32_t n_stages);
+int vr2_tower_workspace_layout(const vr2_tower* tower, int64_t n_patches, int64_t* offsets, int64_t* h_ld);
+
 /* Per-kernel-kind device timing.  vr2_tower_profile(mask) selects kinds (bit k = vr2_kernel_kind k; 0 turns it
  * off) and resets the counters; while selected, vr2_tower_forward brackets every launch of that kind with a
  * cudaEvent pair on the caller's stream.  vr2_tower_profile_read synchronises on those events and returns the

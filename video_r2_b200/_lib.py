@@ -105,6 +105,8 @@ SIGNATURES = {
     "vr2_tower_saturation_counts": (C.c_int, [_P, C.POINTER(C.c_uint64), C.c_int32, _P]),
     "vr2_tower_set_f16_shift": (C.c_int, [_P, C.c_int32, C.c_int32]),
     "vr2_tower_get_f16_shift": (C.c_int, [_P, C.POINTER(C.c_int32)]),
+    "vr2_tower_set_debug_stop": (C.c_int, [_P, C.c_int32]),
+    "vr2_tower_workspace_layout": (C.c_int, [_P, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "vr2_tower_profile": (C.c_int, [_P, C.c_uint32]),
     "vr2_tower_profile_read": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "vr2_tower_launch_count": (C.c_int64, [_P, _P, C.c_int32]),

@@ -87,6 +87,7 @@ struct vr2_tower {
   std::vector<cudaEvent_t> prof_events;  // pairs (begin, end)
   std::vector<int> prof_kind;            // kind of pair i
   size_t prof_used = 0;                  // pairs recorded since the last reset
+  int debug_stop = 0;                    // tests: return from the forward after this many stages (vr2_tower_set_debug_stop)
 };
 
 using namespace vr2;
@@ -471,6 +472,10 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
   const char* alt_env = getenv("VR2_ALTERNATE");   // read per forward: tests toggle it
   const bool alternate = alt_env == nullptr || alt_env[0] != '0';
   int n_launch = 0;
+  // tests (vr2_tower_set_debug_stop): the forward returns after `debug_stop` stages — patch embed, then qkv, attention,
+  // proj, gate|up, down of every block — leaving the workspace as that stage wrote it
+  int n_stage = 0;
+  auto stage_done = [&]() { return t->debug_stop > 0 && ++n_stage >= t->debug_stop; };
   auto G = [&](GemmArgs& a, int kind, const char* what) -> int {
     ProfScope prof(t, kind, s);
     if (alternate && (n_launch++ & 1)) a.flags |= GEMM_REVERSE_M;
@@ -509,6 +514,7 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
     a.sat_wmax2 = NWMAX2(0);
     a.ssq = w.ssq;
     if ((rc = G(a, VR2_K_PATCH_EMBED, "patch_embed")) != VR2_OK) return rc;
+    if (stage_done()) return VR2_OK;
   }
 
   for (int l = 0; l < t->cfg.depth; ++l) {
@@ -525,6 +531,7 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
       a.cos_tab = plan->cos_tab; a.sin_tab = plan->sin_tab;
       a.pos_win = plan->pos_win; a.pos_tab = plan->pos_tab; a.n_pos = plan->n_pos;
       if ((rc = G(a, VR2_K_QKV, "qkv")) != VR2_OK) return rc;
+      if (stage_done()) return VR2_OK;
     }
     {
       const bool full = is_full_layer(t, l);
@@ -536,6 +543,7 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
         VR2_CUDA(attention_tc_launch(w.qkv, w.att, full ? plan->seg_full : plan->seg_window, static_cast<int>(N),
                                      t->cfg.num_heads, 3 * h, h, t->num_sms, s, f16, alternate && (n_launch & 1)));
       ++n_launch;
+      if (stage_done()) return VR2_OK;
     }
     {
       GemmArgs a{};
@@ -548,6 +556,7 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
       a.sat_wmax2 = NWMAX2(2 * l + 1);
       a.ssq = w.ssq;
       if ((rc = G(a, VR2_K_PROJ, "proj")) != VR2_OK) return rc;
+      if (stage_done()) return VR2_OK;
     }
     {
       GemmArgs a{};
@@ -559,6 +568,7 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
       a.ssq_in = w.ssq; a.ssq_parts = parts; a.inv_dim = 1.0f / h; a.eps = eps;
       a.in_scale = xb_back; a.up_scale = h_down;
       if ((rc = G(a, VR2_K_GATE_UP, "gate_up")) != VR2_OK) return rc;
+      if (stage_done()) return VR2_OK;
     }
     {
       GemmArgs a{};
@@ -572,6 +582,7 @@ static int tower_forward_impl(vr2_tower* t, const vr2_plan* plan, const void* pi
       a.in_scale = h_back;
       a.ssq = w.ssq;
       if ((rc = G(a, VR2_K_DOWN, "down")) != VR2_OK) return rc;
+      if (stage_done()) return VR2_OK;
     }
   }
 
@@ -733,6 +744,23 @@ extern "C" int vr2_tower_get_f16_shift(const vr2_tower* t, int32_t* shifts_host)
   if (t == nullptr || shifts_host == nullptr) return fail(VR2_ERR_ARG, "vr2_tower_get_f16_shift: null argument");
   shifts_host[0] = t->shift_xb;
   shifts_host[1] = t->shift_h;
+  return VR2_OK;
+}
+
+extern "C" int vr2_tower_set_debug_stop(vr2_tower* t, int32_t n_stages) {
+  if (t == nullptr || n_stages < 0) return fail(VR2_ERR_ARG, "vr2_tower_set_debug_stop: null tower or negative count");
+  t->debug_stop = n_stages;
+  return VR2_OK;
+}
+
+extern "C" int vr2_tower_workspace_layout(const vr2_tower* t, int64_t n_patches, int64_t* offsets, int64_t* h_ld) {
+  if (t == nullptr || offsets == nullptr || h_ld == nullptr || n_patches <= 0)
+    return fail(VR2_ERR_ARG, "vr2_tower_workspace_layout: null argument");
+  char* base = reinterpret_cast<char*>(static_cast<uintptr_t>(1024));   // only differences of the carved pointers are used
+  const Workspace w = carve_ws(t, n_patches, base);
+  const void* p[7] = {w.x, w.xb, w.qkv, w.att, w.hbuf, w.ssq, w.pix};
+  for (int i = 0; i < 7; ++i) offsets[i] = static_cast<const char*>(p[i]) - base;
+  *h_ld = t->ipad;
   return VR2_OK;
 }
 

@@ -471,6 +471,28 @@ class VisionTower:
     KERNEL_KINDS = ("cast", "patch_embed", "qkv", "attn_window", "attn_full", "proj", "gate_up", "down",
                     "merger_norm", "fc1", "fc2")
 
+    # ------------------------------------------------------------------ test hooks (stage-by-stage parity)
+    def debug_stop(self, n_stages: int):
+        """Every following forward returns after n stages (1 = patch embed, then qkv, attention, proj, gate|up, down of
+        block 0, ...), leaving the workspace as that stage wrote it; 0 turns it off (include/vr2.h)."""
+        check(lib().vr2_tower_set_debug_stop(self._h, int(n_stages)), "vr2_tower_set_debug_stop")
+
+    def debug_buffers(self, n_patches: int) -> dict:
+        """Views of the workspace of the LAST forward of n_patches rows (window order): x fp32 [N, hidden], xb / qkv / att
+        / h in the activation format of the current precision, ssq fp32 [hidden / 40, N] (partial sums of x^2; how many
+        leading rows are live depends on the kernel that wrote them)."""
+        off = (C.c_int64 * 7)()
+        h_ld = C.c_int64(0)
+        check(lib().vr2_tower_workspace_layout(self._h, int(n_patches), off, C.byref(h_ld)), "vr2_tower_workspace_layout")
+        ws, n, hd = self._ws, int(n_patches), self.cfg.hidden_size
+        act = torch.float16 if self.precision in ("f16", "auto") else torch.bfloat16
+
+        def view(i, dtype, rows, cols):
+            nbytes = rows * cols * torch.empty((), dtype=dtype).element_size()
+            return ws[off[i]: off[i] + nbytes].view(dtype).reshape(rows, cols)
+        return {"x": view(0, torch.float32, n, hd), "xb": view(1, act, n, hd), "qkv": view(2, act, n, 3 * hd),
+                "att": view(3, act, n, hd), "h": view(4, act, n, int(h_ld.value)), "ssq": view(5, torch.float32, hd // 40, n)}
+
     def profile(self, kinds=()):
         """Select kernel kinds to time with CUDA events inside forward (() turns profiling off)."""
         mask = 0
