@@ -122,3 +122,15 @@ def test_every_stage_of_two_blocks(prec):
         nxt = Wd["blocks.1.norm1.weight"] if l == 0 else Wd["merger.ln_q.weight"]
         check_resid(dn, x2, nxt, 5, f"down[{l}]")
         prev, stage, parts = dn, stage + 5, 5
+
+    # ---- PatchMerger on the kernel's own final residual stream: ln_q -> 16 bit, fc1 + GELU(erf) -> 16 bit, fc2 in fp32,
+    #      rows back in the original token order (HF :133-146, :512-513)
+    out = tower(pix, GRID, out_dtype=torch.float32)
+    x = prev["x"]
+    y = (Wd["merger.ln_q.weight"] * (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps))).to(act).float()
+    hid = torch.nn.functional.gelu(y.reshape(n // 4, 4 * hd) @ Wd["merger.mlp.0.weight"].T + Wd["merger.mlp.0.bias"])
+    ref = hid.to(act).float() @ Wd["merger.mlp.2.weight"].T + Wd["merger.mlp.2.bias"]
+    ref = ref[ex["reverse_index"]]
+    err = (out - ref).abs().max().item()
+    # the two 16-bit roundings are reproduced above; what is left are last-bit flips of them and the summation order
+    assert err < (2e-2 if prec == "bf16" else 3e-3), ("merger", prec, err)
