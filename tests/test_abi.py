@@ -57,3 +57,17 @@ def test_compute_fails_loudly_without_gpu():
         vr2.VisionTower(vr2.VisionConfig(depth=1), {}, device="cuda:0")
     with pytest.raises(Exception):
         vr2.get_rope_index(torch.zeros(1, 4, dtype=torch.int64))
+
+
+def test_bind_to_gpu_node_changes_nothing_without_a_gpu():
+    """HostPipeline's NUMA helper is best effort: without NVML / a visible GPU it returns [] and leaves the affinity."""
+    import os
+    import video_r2_b200 as vr2
+    before = os.sched_getaffinity(0)
+    cores = vr2.bind_to_gpu_node("cuda:0")
+    assert isinstance(cores, list)
+    if not cores:
+        assert os.sched_getaffinity(0) == before
+    else:   # a GPU box: bound to a subset of what was allowed
+        assert set(cores) <= before and os.sched_getaffinity(0) == set(cores)
+        os.sched_setaffinity(0, before)
